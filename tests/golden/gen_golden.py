@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""Generate golden vectors from the UNMODIFIED reference (cruzas/DD4ML).
+
+Run in the authoring container only (needs /root/reference):
+
+    OMP_NUM_THREADS=1 python tests/golden/gen_golden.py
+
+The reference cannot travel to the GPU box, so the outputs (tests/golden/*.npz)
+are committed.  Everything here drives the reference's own classes
+(`dd4ml.optimizers.{tr,lssr1_tr,apts_d,apts_p,apts_pinn}`) through their public
+API on synthetic tensors with fixed seeds; nothing is re-implemented.
+Recorded: torch version, thread count, seeds, per-step scalars, and for the first
+few sub-problem solves the full input/output vectors.
+"""
+import math
+import os
+import sys
+
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+sys.path.insert(0, "/root/reference/src")
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+import dd4ml.utility  # noqa: F401  (must precede dd4ml.optimizers: circular import)
+from dd4ml.models.ffnn.medium_ffnn import MediumFFNN
+from dd4ml.optimizers import lssr1_tr as ref_lssr1_mod
+from dd4ml.optimizers import tr as ref_tr_mod
+from dd4ml.optimizers.apts_d import APTS_D
+from dd4ml.optimizers.apts_p import APTS_P
+from dd4ml.optimizers.apts_pinn import APTS_PINN
+from dd4ml.optimizers.lsr1 import LSR1
+from dd4ml.optimizers.lssr1_tr import LSSR1_TR
+from dd4ml.optimizers.tr import TR
+from dd4ml.solvers.obs import OBS
+from dd4ml.utility import CfgNode, set_seed
+from dd4ml.utility.optimizer_utils import solve_tr_second_order as ref_solve_so
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+IN_F, HID, OUT = 36, [12, 12], 10          # tiny FFNN: n = 730
+MAX_SOLVES = 8
+
+
+def make_model(dtype=torch.float32):
+    set_seed(42)
+    cfg = MediumFFNN.get_default_config()
+    cfg.input_features, cfg.fc_layers, cfg.output_classes = IN_F, list(HID), OUT
+    return MediumFFNN(cfg).to(dtype)
+
+
+def make_data(n_samples, seed=1234, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randn(n_samples, 1, 6, 6, generator=g).to(dtype)
+    Y = torch.randint(0, OUT, (n_samples,), generator=g)
+    return X, Y
+
+
+def flat(model):
+    return torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+
+
+# ------------------------------------------------------------------ capture
+class SolveRecorder:
+    """Wraps solve_tr_second_order / OBS.Newton as imported into the optimizer modules."""
+
+    def __init__(self):
+        self.recs = []
+        self._newton = []
+        self._orig_newton = OBS.Newton
+
+    def __enter__(self):
+        rec = self
+
+        def newton(obs, x0, Lam, a, delta):
+            out = rec._orig_newton(obs, x0, Lam, a, delta)
+            rec._newton.append((float(x0), float(out), Lam.clone(), a.clone()))
+            return out
+
+        def solve(gradient, grad_norm, trust_radius, lsr1_hessian, obs_solver, tol, dogleg=False):
+            rec._newton.clear()
+            p, pred = ref_solve_so(gradient=gradient, grad_norm=grad_norm, trust_radius=trust_radius,
+                                   lsr1_hessian=lsr1_hessian, obs_solver=obs_solver, tol=tol, dogleg=dogleg)
+            if len(rec.recs) < MAX_SOLVES:
+                k = lsr1_hessian._current_pairs
+                r = dict(g=gradient.clone(), gn=float(grad_norm), delta=float(trust_radius),
+                         gamma=float(lsr1_hessian.gamma), S=lsr1_hessian._S_matrix[:, :k].clone(),
+                         Y=lsr1_hessian._Y_matrix[:, :k].clone(), p=p.clone(), pred=float(pred),
+                         dogleg=int(dogleg), tol=float(tol), newton=int(len(rec._newton) > 0))
+                if rec._newton:
+                    x0, sig, Lam, a = rec._newton[-1]
+                    r.update(x0=x0, sigma=sig, Lam=Lam, a=a)
+                rec.recs.append(r)
+            return p, pred
+
+        OBS.Newton = newton
+        ref_tr_mod.solve_tr_second_order = solve
+        ref_lssr1_mod.solve_tr_second_order = solve
+        return self
+
+    def __exit__(self, *exc):
+        OBS.Newton = self._orig_newton
+        ref_tr_mod.solve_tr_second_order = ref_solve_so
+        ref_lssr1_mod.solve_tr_second_order = ref_solve_so
+
+    def dump(self, out):
+        out["n_solves"] = np.int64(len(self.recs))
+        for i, r in enumerate(self.recs):
+            for k, v in r.items():
+                out[f"solve{i}_{k}"] = v.numpy() if torch.is_tensor(v) else np.asarray(v)
+
+
+def meta(out, **kw):
+    out["torch_version"] = np.asarray(torch.__version__)
+    out["omp_threads"] = np.int64(torch.get_num_threads())
+    for k, v in kw.items():
+        out[k] = np.asarray(v)
+
+
+def save(name, out):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.0f} KB)")
+
+
+# ------------------------------------------------------------------ scenarios
+def tr_kwargs(second_order, dogleg, norm_type=2):
+    cfg = CfgNode(delta=0.1, max_delta=2.0, min_delta=1e-3, norm_type=norm_type,
+                  glob_second_order=second_order, glob_dogleg=dogleg, tol=1e-6)
+    from dd4ml.utility import get_tr_hparams
+    return get_tr_hparams(cfg)
+
+
+def run_plain(name, make_opt, steps, dtype=torch.float32):
+    """Plain TR / LSSR1_TR as the top-level optimizer with an own closure."""
+    model = make_model(dtype)
+    X, Y = make_data(256, dtype=dtype)
+    crit = nn.CrossEntropyLoss()
+    opt = make_opt(model)
+
+    def closure(compute_grad=True):
+        opt.zero_grad()
+        loss = crit(model(X), Y)
+        if compute_grad:
+            loss.backward()
+        return loss
+
+    out = {"w0": flat(model).numpy(), "X": X.numpy(), "Y": Y.numpy()}
+    losses, deltas, ws = [], [], []
+    with SolveRecorder() as rec:
+        for _ in range(steps):
+            loss, _g = opt.step(closure)
+            losses.append(float(loss))
+            deltas.append(float(opt.delta))
+            ws.append(flat(model).numpy())
+        rec.dump(out)
+    out["loss"] = np.asarray(losses)
+    out["delta"] = np.asarray(deltas)
+    out["w_step1"] = ws[0]
+    out["w_step5"] = ws[4]
+    out["w_final"] = ws[-1]
+    if getattr(opt, "hess", None) is not None:
+        out["final_pairs"] = np.int64(len(opt.hess._S))
+        out["final_gamma"] = np.float64(float(opt.hess.gamma))
+    meta(out, steps=steps)
+    save(name, out)
+
+
+def apts_cfg(glob, loc, so, dog, m, norm_type=2, delta=0.1, min_delta=0.01, max_delta=1.0):
+    return CfgNode(delta=delta, min_delta=min_delta, max_delta=max_delta, norm_type=norm_type,
+                   glob_second_order=so, glob_dogleg=dog, loc_second_order=so, loc_dogleg=dog,
+                   mem_length=m, max_wolfe_iters=5, max_zoom_iters=5, tol=1e-6,
+                   paper_tr_update=False, glob_opt=glob, loc_opt=loc, learning_rate=0.1)
+
+
+def _apts_worker(rank, ws, port, kind, glob, loc, so, dog, m, steps, dtype, q):
+    torch.set_num_threads(1)
+    if ws > 1 or kind == "apts_p":
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=ws)
+    model = make_model(dtype)
+    per = 128
+    X, Y = make_data(per * ws, dtype=dtype)
+    crit = nn.CrossEntropyLoss()
+    norm_type = math.inf if kind == "apts_p" else 2
+    kw = dict(delta=0.1, min_delta=0.01, max_delta=0.5) if kind == "apts_p" else {}
+    cfg = apts_cfg(glob, loc, so, dog, m, norm_type=norm_type, **kw)
+    cls = APTS_D if kind == "apts_d" else APTS_P
+    cfg = cls.setup_APTS_hparams(cfg)
+    extra = dict(foc=True) if kind == "apts_d" else {}
+    opt = cls(model.parameters(), model=model, criterion=crit, device="cpu", nr_models=ws,
+              glob_opt=cfg.glob_opt, glob_opt_hparams=cfg.glob_opt_hparams, loc_opt=cfg.loc_opt,
+              loc_opt_hparams=cfg.loc_opt_hparams, glob_pass=True, norm_type=norm_type,
+              max_loc_iters=3, max_glob_iters=1, tol=1e-6, **extra, **cfg.apts_params)
+    if kind == "apts_d":
+        Xr, Yr = X[rank * per:(rank + 1) * per], Y[rank * per:(rank + 1) * per]
+    else:
+        Xr, Yr = X, Y           # APTS_P: every rank evaluates the same batch
+    out = {"w0": flat(model).numpy(), "X": X.numpy(), "Y": Y.numpy()}
+    if kind == "apts_p":
+        out["owned_tensors"] = np.asarray(sorted(int(i) for i in opt.loc_model._trainable_indices))
+    losses, deltas, gdeltas, ldeltas, gevals, ws_hist = [], [], [], [], [], []
+    for _ in range(steps):
+        loss = opt.step(Xr, Yr)
+        losses.append(float(loss))
+        deltas.append(float(opt.delta))
+        gdeltas.append(float(opt.glob_opt.delta))
+        ldeltas.append(float(opt.loc_opt.delta))
+        gevals.append(float(opt.grad_evals))
+        ws_hist.append(flat(model).numpy())
+    out.update(loss=np.asarray(losses), delta=np.asarray(deltas), glob_delta=np.asarray(gdeltas),
+               loc_delta=np.asarray(ldeltas), grad_evals=np.asarray(gevals),
+               w_step1=ws_hist[0], w_step3=ws_hist[2], w_final=ws_hist[-1])
+    q.put((rank, out))
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_apts(name, kind, ws, glob, loc, so, dog, m, steps, dtype=torch.float32, port=29611):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_apts_worker,
+                         args=(r, ws, port, kind, glob, loc, so, dog, m, steps, dtype, q))
+             for r in range(ws)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get() for _ in range(ws))
+    for p in procs:
+        p.join()
+    out = outs[0]
+    if kind == "apts_p":
+        for r in range(ws):
+            out[f"owned_tensors_rank{r}"] = outs[r]["owned_tensors"]
+    for r in range(1, ws):      # the global model must be identical on every rank
+        assert np.array_equal(outs[r]["w_final"], out["w_final"]), "ranks diverged"
+    meta(out, steps=steps, world_size=ws, glob=glob, loc=loc, second_order=int(so),
+         dogleg=int(dog), mem_length=m, kind=kind)
+    save(name, out)
+
+
+class SineCrit(nn.Module):
+    """PINN-like criterion for APTS_PINN: reads the collocation points from
+    `current_x` (set by APTS_PINN._set_criterion_input), ignores the (long) labels."""
+    low, high = 0.0, 1.0
+
+    def __init__(self):
+        super().__init__()
+        self.current_x = None
+
+    def forward(self, out, labels):
+        return ((out.squeeze(-1) - torch.sin(2 * math.pi * self.current_x.squeeze(-1))) ** 2).mean()
+
+
+def _pinn_worker(rank, ws, port, steps, q):
+    torch.set_num_threads(1)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    set_seed(42)
+    cfg = MediumFFNN.get_default_config()
+    cfg.input_features, cfg.fc_layers, cfg.output_classes = 1, [16, 16], 1
+
+    class Net(MediumFFNN):          # same stack, linear head instead of log_softmax
+        def forward(self, x):
+            x = x.view(x.size(0), -1)
+            for i in range(1, len(self.config.fc_layers) + 1):
+                x = getattr(self, f"stage{i}")(x)
+            return self.finish(x)
+
+    globals()["Net"] = Net
+    model = Net(cfg)
+    crit = SineCrit()
+    x = torch.linspace(0, 1, 65).unsqueeze(1)
+    lab = torch.zeros(65, 1)
+    tr_kw = dict(delta=0.1, nu_dec=0.25, nu_inc=0.75, inc_factor=1.2, dec_factor=0.9,
+                 max_delta=2.0, min_delta=1e-3, tol=1e-6)
+    opt = APTS_PINN(model.parameters(), model=model, criterion=crit, device="cpu", glob_opt=TR,
+                    glob_opt_hparams=tr_kw, loc_opt=TR, loc_opt_hparams=tr_kw, glob_pass=True,
+                    foc=True, norm_type=2, max_loc_iters=4, max_glob_iters=1, num_subdomains=ws,
+                    overlap=0.1, **tr_kw)
+    out = {"w0": flat(model).numpy(), "x": x.numpy()}
+    losses, deltas = [], []
+    for _ in range(steps):
+        loss = opt.step(inputs=x, labels=lab)
+        losses.append(float(loss))
+        deltas.append(float(opt.delta))
+    out.update(loss=np.asarray(losses), delta=np.asarray(deltas), w_final=flat(model).numpy())
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_pinn(name, ws, steps, port=29631):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pinn_worker, args=(r, ws, port, steps, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get() for _ in range(ws))
+    for p in procs:
+        p.join()
+    out = outs[0]
+    meta(out, steps=steps, world_size=ws, overlap=0.1)
+    save(name, out)
+
+
+def run_kernel_level(name):
+    """Direct calls of LSR1.update_memory / precompute / B and solve_tr_second_order on
+    synthetic (s, y) pairs: y = A s for a fixed indefinite diagonal-plus-low-rank A."""
+    torch.manual_seed(7)
+    n = 512
+    diag = torch.linspace(-0.5, 3.0, n)
+    Ulr = torch.randn(n, 4) / math.sqrt(n)
+    A = lambda v: diag * v + Ulr @ (Ulr.t() @ v)
+    out = {}
+    idx = 0
+    for m in (1, 3, 5):
+        hess = LSR1(gamma=1.0, memory_length=m, tol=1e-6)
+        accepted = []
+        for j in range(m + 2):
+            s = torch.randn(n) * 0.05
+            y = A(s) + 1e-3 * torch.randn(n)
+            before = len(hess._S)
+            g_before = float(hess.gamma)
+            hess.update_memory(s, y)
+            accepted.append(int(float(hess.gamma) != g_before or len(hess._S) != before))
+            hess.precompute()
+            out[f"upd{idx}_s"], out[f"upd{idx}_y"] = s.numpy(), y.numpy()
+            out[f"upd{idx}_m"], out[f"upd{idx}_accepted"] = np.int64(m), np.int64(accepted[-1])
+            out[f"upd{idx}_gamma"] = np.float64(float(hess.gamma))
+            out[f"upd{idx}_Minv"] = hess.Minv.numpy().copy()
+            v = torch.randn(n)
+            out[f"upd{idx}_v"], out[f"upd{idx}_Bv"] = v.numpy(), hess.B(v).numpy()
+            idx += 1
+        for dog in (False, True):
+            for delta in (0.01, 0.3, 5.0, 100.0):
+                g = torch.randn(n)
+                obs = OBS()
+                newt = []
+                orig = OBS.Newton
+
+                def newton(o, x0, Lam, a, d, _n=newt):
+                    r = orig(o, x0, Lam, a, d)
+                    _n.append((float(x0), float(r), Lam.clone(), a.clone()))
+                    return r
+                OBS.Newton = newton
+                p, pred = ref_solve_so(g, torch.norm(g), delta, hess, obs, 1e-6, dogleg=dog)
+                OBS.Newton = orig
+                key = f"so_m{m}_dog{int(dog)}_d{delta}"
+                k = hess._current_pairs
+                out[key + "_g"], out[key + "_p"] = g.numpy(), p.numpy()
+                out[key + "_pred"] = np.float64(float(pred))
+                out[key + "_S"] = hess._S_matrix[:, :k].numpy().copy()
+                out[key + "_Y"] = hess._Y_matrix[:, :k].numpy().copy()
+                out[key + "_gamma"] = np.float64(float(hess.gamma))
+                out[key + "_newton"] = np.int64(len(newt))
+                if newt:
+                    out[key + "_x0"], out[key + "_sigma"] = np.float64(newt[-1][0]), np.float64(newt[-1][1])
+                    out[key + "_Lam"], out[key + "_a"] = newt[-1][2].numpy(), newt[-1][3].numpy()
+    out["n_updates"] = np.int64(idx)
+    meta(out)
+    save(name, out)
+
+
+def main():
+    torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+    run_kernel_level("kernel_level")
+    run_plain("tr_fo", lambda m: TR(m.parameters(), **tr_kwargs(False, False)), 30)
+    run_plain("tr_fo_inf", lambda m: TR(m.parameters(), **tr_kwargs(False, False, math.inf)), 12)
+    run_plain("tr_so", lambda m: TR(m.parameters(), **tr_kwargs(True, False)), 30)
+    run_plain("tr_so_dogleg", lambda m: TR(m.parameters(), **tr_kwargs(True, True)), 30)
+    from dd4ml.utility import get_lssr1_tr_hparams
+    for dog in (False, True):
+        hp = get_lssr1_tr_hparams(apts_cfg("lssr1_tr", "lssr1_tr", True, dog, 3))
+        hp["sync"] = False
+        run_plain(f"lssr1_so_dog{int(dog)}", lambda m, hp=hp: LSSR1_TR(m.parameters(), **hp), 30)
+    hp = get_lssr1_tr_hparams(apts_cfg("lssr1_tr", "lssr1_tr", False, False, 3))
+    hp["sync"] = False
+    run_plain("lssr1_fo", lambda m: LSSR1_TR(m.parameters(), **hp), 20)
+    hp = dict(hp, paper_tr_update=True, second_order=True)
+    run_plain("lssr1_paper", lambda m: LSSR1_TR(m.parameters(), **hp), 20)
+    run_apts("apts_d_tr_fo_ws1", "apts_d", 1, "tr", "tr", False, False, 3, 12, port=29601)
+    run_apts("apts_d_tr_fo_ws2", "apts_d", 2, "tr", "tr", False, False, 3, 12, port=29602)
+    run_apts("apts_d_tr_so_ws2", "apts_d", 2, "tr", "tr", True, False, 3, 12, port=29603)
+    run_apts("apts_d_lssr1_so_ws2", "apts_d", 2, "lssr1_tr", "lssr1_tr", True, True, 3, 12, port=29604)
+    run_apts("apts_d_lssr1_fo_ws4", "apts_d", 4, "lssr1_tr", "lssr1_tr", False, False, 3, 8, port=29605)
+    run_apts("apts_p_tr_fo_ws2", "apts_p", 2, "tr", "tr", False, False, 3, 12, port=29606)
+    run_apts("apts_p_tr_fo_ws2_f64", "apts_p", 2, "tr", "tr", False, False, 3, 12,
+             dtype=torch.float64, port=29607)
+    run_apts("apts_p_tr_so_ws2", "apts_p", 2, "tr", "tr", True, False, 3, 12, port=29608)
+    run_pinn("apts_pinn_ws2", 2, 10, port=29609)
+
+
+if __name__ == "__main__":
+    main()
