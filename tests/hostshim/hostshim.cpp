@@ -1,0 +1,40 @@
+// TEST INFRASTRUCTURE ONLY: compiles dd4ml_b200/csrc/kspace.h for the host so that the
+// k-space routines (the exact source the CUDA kernels run in their last CTA) can be
+// checked against the oracle without a GPU.  Never loaded by the product package.
+#include "../../dd4ml_b200/csrc/kspace.h"
+#include "../../dd4ml_b200/csrc/state_table.h"
+
+extern "C" {
+int hostshim_state_doubles() { return (int)(sizeof(dd4ml_state) / sizeof(double)); }
+int hostshim_num_fields() { return DD4ML_NUM_FIELDS; }
+int hostshim_field(int i, const char** name, int* offset, int* count) {
+    if (i < 0 || i >= DD4ML_NUM_FIELDS) return 1;
+    *name = DD4ML_FIELD_TABLE[i].name;
+    *offset = DD4ML_FIELD_TABLE[i].offset;
+    *count = DD4ML_FIELD_TABLE[i].count;
+    return 0;
+}
+void hostshim_tr_solve(double* st, int mode, int is_float) {
+    if (is_float) ks::tr_solve<float>((dd4ml_state*)st, mode);
+    else ks::tr_solve<double>((dd4ml_state*)st, mode);
+}
+int hostshim_try_update(double* st) { return ks::lsr1_try_update((dd4ml_state*)st) ? 1 : 0; }
+void hostshim_tr_finish(double* st, double loss, double trial, int is_float) {
+    dd4ml_state* s = (dd4ml_state*)st;
+    double rho;
+    bool acc = is_float ? ks::tr_accept<float>(loss, trial, s->pred[0], s->tol[0], s->nu_dec[0], &rho)
+                        : ks::tr_accept<double>(loss, trial, s->pred[0], s->tol[0], s->nu_dec[0], &rho);
+    if (is_float) ks::tr_finish<float>(s, acc, rho); else ks::tr_finish<double>(s, acc, rho);
+}
+int hostshim_apts_control(double* st, double f0, double ft, double pred, int is_float) {
+    return (is_float ? ks::apts_control<float>((dd4ml_state*)st, f0, ft, pred)
+                     : ks::apts_control<double>((dd4ml_state*)st, f0, ft, pred)) ? 1 : 0;
+}
+int hostshim_eigh(const double* A, int k, double* w, double* V) {
+    double a[ks::M * ks::M], v[ks::M * ks::M], ww[ks::M];
+    for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) a[i * ks::M + j] = A[i * k + j];
+    ks::jacobi_eigh(a, k, ww, v);
+    for (int i = 0; i < k; ++i) { w[i] = ww[i]; for (int j = 0; j < k; ++j) V[i * k + j] = v[i * ks::M + j]; }
+    return 0;
+}
+}
