@@ -1,0 +1,139 @@
+"""ctypes binding of ``libdd4ml_b200.so`` (C ABI declared in ``include/dd4ml_b200.h``).
+
+There is no CPU fallback: if the shared library is missing and cannot be built, or a
+tensor is not on a CUDA device, the product raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_int64, c_void_p
+
+import torch
+
+from ._state import StateLayout
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libdd4ml_b200.so")
+
+F32, F64 = 0, 1
+_DT = {torch.float32: F32, torch.float64: F64}
+
+
+class DD4MLError(RuntimeError):
+    pass
+
+
+def dt(dtype: torch.dtype) -> int:
+    try:
+        return _DT[dtype]
+    except KeyError:
+        raise DD4MLError(f"dd4ml_b200: unsupported dtype {dtype} (float32 / float64 only)")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise DD4MLError("dd4ml_b200 has no CPU path: tensor must live on a CUDA device")
+    if not t.is_contiguous():
+        raise DD4MLError("dd4ml_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+_SIGS = {
+    "dd4ml_version": ([], c_int),
+    "dd4ml_error_string": ([c_int], c_char_p),
+    "dd4ml_state_doubles": ([], c_int),
+    "dd4ml_workspace_doubles": ([], c_int),
+    "dd4ml_num_fields": ([], c_int),
+    "dd4ml_max_mem_length": ([], c_int),
+    "dd4ml_state_init": ([c_void_p, c_void_p, c_double, c_void_p], c_int),
+    "dd4ml_state_set": ([c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double), c_void_p], c_int),
+    "dd4ml_tr_propose": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
+    "dd4ml_tr_apply": ([c_void_p] * 7 + [c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
+    "dd4ml_tr_decide": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 7 + [c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
+    "dd4ml_lsr1_update": ([c_void_p] * 6 + [c_int64, c_int64, c_int, c_int, c_void_p], c_int),
+    "dd4ml_lsr1_B": ([c_void_p] * 6 + [c_int64, c_int64, c_int, c_int, c_void_p], c_int),
+    "dd4ml_lssr1_begin": ([c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
+    "dd4ml_lssr1_trial": ([c_void_p, c_void_p, c_void_p, c_double, c_int64, c_int, c_int, c_void_p], c_int),
+    "dd4ml_lssr1_eval": ([c_void_p] * 6 + [c_int, c_int64, c_int, c_void_p], c_int),
+    "dd4ml_apts_residual": ([c_void_p] * 5 + [c_int64, c_int, c_void_p], c_int),
+    "dd4ml_apts_foc": ([c_void_p] * 7 + [c_int, c_double, c_int64, c_int, c_int, c_void_p], c_int),
+    "dd4ml_apts_pack": ([c_void_p] * 5 + [c_int, c_double, c_double, c_int64, c_int, c_void_p], c_int),
+    "dd4ml_apts_trial": ([c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_int64, c_int, c_void_p], c_int),
+    "dd4ml_apts_control": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int, c_void_p], c_int),
+    "dd4ml_gather": ([c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int, c_void_p], c_int),
+    "dd4ml_seg_copy": ([c_void_p, c_void_p, c_int, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int64, c_int, c_int, c_void_p], c_int),
+}
+
+EXPORTS = tuple(_SIGS) + ("dd4ml_field",)
+
+
+class Lib:
+    """Thin checked wrapper: ``lib.tr_propose(...)`` raises DD4MLError on a non-zero return."""
+
+    def __init__(self, path: str = _SO):
+        if not os.path.exists(path):
+            from . import build as _build  # nvcc is part of the image; the .so normally ships prebuilt
+            try:
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise DD4MLError(
+                    f"dd4ml_b200: CUDA extension {path} is missing and could not be built ({e}); "
+                    "there is no CPU fallback") from e
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(self.cdll, name)
+            fn.argtypes, fn.restype = args, res
+        self.layout = StateLayout(self.cdll, prefix="dd4ml_")
+        self.state_doubles = self.cdll.dd4ml_state_doubles()
+        self.workspace_doubles = self.cdll.dd4ml_workspace_doubles()
+        self.max_mem_length = self.cdll.dd4ml_max_mem_length()
+        self.launches = 0  # kernels enqueued through this binding (bench.py's gpu_launches)
+        self.prof = None   # bench.py: {entry point: [(start_event, end_event), ...]} when profiling
+
+    def _call(self, name, launches, *args):
+        if self.prof is not None and launches:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = getattr(self.cdll, name)(*args)
+            e1.record()
+            self.prof.setdefault(name, []).append((e0, e1))
+        else:
+            rc = getattr(self.cdll, name)(*args)
+        if rc != 0:
+            msg = self.cdll.dd4ml_error_string(rc)
+            raise DD4MLError(f"{name} failed: {msg.decode() if msg else rc} (code {rc})")
+        self.launches += launches
+
+    def __getattr__(self, short):
+        name = "dd4ml_" + short
+        if name not in _SIGS:
+            raise AttributeError(short)
+        launches = _LAUNCHES.get(short, 1)
+
+        def call(*args):
+            return self._call(name, launches, *args)
+
+        self.__dict__[short] = call
+        return call
+
+
+# kernels launched per entry point
+_LAUNCHES = {"state_init": 2, "lsr1_B": 2, "version": 0, "error_string": 0}
+
+_LIB: Lib | None = None
+
+
+def get() -> Lib:
+    global _LIB
+    if _LIB is None:
+        _LIB = Lib()
+    return _LIB

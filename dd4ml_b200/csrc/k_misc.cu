@@ -1,0 +1,164 @@
+// dd4ml_b200 -- state block plumbing, multi-tensor gather / segmented copy, introspection.
+#include "stream.cuh"
+#include "state_table.h"
+
+namespace {
+
+constexpr int GATHER_MAX = 96;
+struct GatherTable {
+    const void* src[GATHER_MAX];
+    int64_t off[GATHER_MAX];
+    int64_t len[GATHER_MAX];
+    int count;
+};
+template <class T>
+__global__ void __launch_bounds__(BLOCK) gather_kernel(T* dst, GatherTable tb) {
+    // blockIdx.y = tensor, blockIdx.x strides over its elements
+    const int t = blockIdx.y;
+    const T* s = reinterpret_cast<const T*>(tb.src[t]);
+    T* d = dst + tb.off[t];
+    const int64_t len = tb.len[t];
+    for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < len; i += (int64_t)gridDim.x * BLOCK) d[i] = s[i];
+}
+
+constexpr int SEG_MAX = 96;
+struct SegTable {
+    int64_t dst_off[SEG_MAX];
+    int64_t src_off[SEG_MAX];
+    int64_t len[SEG_MAX];
+    int count;
+};
+template <class T>
+__global__ void __launch_bounds__(BLOCK) seg_copy_kernel(T* dst, const T* src, SegTable tb) {
+    const int t = blockIdx.y;
+    const T* s = src + tb.src_off[t];
+    T* d = dst + tb.dst_off[t];
+    const int64_t len = tb.len[t];
+    for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < len; i += (int64_t)gridDim.x * BLOCK) d[i] = s[i];
+}
+
+constexpr int SET_MAX = 32;
+struct SetTable {
+    int off[SET_MAX];
+    double val[SET_MAX];
+    int count;
+};
+__global__ void state_set_kernel(double* st, SetTable tb) {
+    const int i = threadIdx.x;
+    if (i < tb.count) st[tb.off[i]] = tb.val[i];
+}
+__global__ void state_init_kernel(double* st, int nst, double* ws, int nws) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nst; i += gridDim.x * blockDim.x) st[i] = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nws; i += gridDim.x * blockDim.x) ws[i] = 0.0;
+}
+__global__ void state_defaults_kernel(dd4ml_state* st, double gamma0) {
+    st->gamma[0] = gamma0;
+    st->spare[0] = 0.0;
+    st->k[0] = 0.0;
+    st->clip_scale[0] = 1.0;
+}
+
+
+}  // namespace
+
+extern "C" {
+
+const char* dd4ml_error_string(int code) {
+    switch (code) {
+        case 0: return "success";
+        case DD4ML_E_DTYPE: return "dd4ml_b200: unsupported dtype combination";
+        case DD4ML_E_ARG: return "dd4ml_b200: bad argument";
+        case DD4ML_E_ALIGN: return "dd4ml_b200: misaligned pointer";
+        default: return cudaGetErrorString((cudaError_t)code);
+    }
+}
+
+int dd4ml_version(void) { return 100; }
+int dd4ml_state_doubles(void) { return (int)(sizeof(dd4ml_state) / sizeof(double)); }
+int dd4ml_workspace_doubles(void) { return WS_DOUBLES; }
+int dd4ml_num_fields(void) { return DD4ML_NUM_FIELDS; }
+int dd4ml_max_mem_length(void) { return DD4ML_MAXM; }
+int dd4ml_field(int i, const char** name, int* offset, int* count) {
+    if (i < 0 || i >= DD4ML_NUM_FIELDS) return DD4ML_E_ARG;
+    *name = DD4ML_FIELD_TABLE[i].name;
+    *offset = DD4ML_FIELD_TABLE[i].offset;
+    *count = DD4ML_FIELD_TABLE[i].count;
+    return 0;
+}
+
+int dd4ml_state_init(double* state, double* ws, double gamma0, void* stream) {
+    if (!state || !ws) return DD4ML_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    state_init_kernel<<<32, 256, 0, s>>>(state, dd4ml_state_doubles(), ws, WS_DOUBLES);
+    state_defaults_kernel<<<1, 1, 0, s>>>((dd4ml_state*)state, gamma0);
+    return (int)cudaGetLastError();
+}
+
+int dd4ml_state_set(double* state, int count, const int* offsets, const double* values, void* stream) {
+    if (!state || count < 0 || count > SET_MAX) return DD4ML_E_ARG;
+    SetTable tb;
+    tb.count = count;
+    const int nst = dd4ml_state_doubles();
+    for (int i = 0; i < count; ++i) {
+        if (offsets[i] < 0 || offsets[i] >= nst) return DD4ML_E_ARG;
+        tb.off[i] = offsets[i];
+        tb.val[i] = values[i];
+    }
+    state_set_kernel<<<1, SET_MAX, 0, (cudaStream_t)stream>>>(state, tb);
+    return (int)cudaGetLastError();
+}
+
+int dd4ml_gather(void* dst, int count, const void* const* srcs, const int64_t* offsets,
+                 const int64_t* lens, int dtype, void* stream) {
+    if (!dst || count < 0 || (dtype != 0 && dtype != 1)) return DD4ML_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int base = 0; base < count; base += GATHER_MAX) {
+        GatherTable tb;
+        tb.count = (count - base < GATHER_MAX) ? count - base : GATHER_MAX;
+        int64_t maxlen = 1;
+        for (int i = 0; i < tb.count; ++i) {
+            tb.src[i] = srcs[base + i];
+            tb.off[i] = offsets[base + i];
+            tb.len[i] = lens[base + i];
+            if (tb.len[i] > maxlen) maxlen = tb.len[i];
+        }
+        int gx = (int)((maxlen + BLOCK * 8 - 1) / (BLOCK * 8));
+        if (gx < 1) gx = 1;
+        if (gx > 64) gx = 64;
+        dim3 grid(gx, tb.count);
+        if (dtype == 0) gather_kernel<float><<<grid, BLOCK, 0, s>>>((float*)dst, tb);
+        else gather_kernel<double><<<grid, BLOCK, 0, s>>>((double*)dst, tb);
+    }
+    return (int)cudaGetLastError();
+}
+
+int dd4ml_seg_copy(void* dst, const void* src, int count, const int64_t* dst_off,
+                   const int64_t* src_off, const int64_t* lens, int64_t n_dst, int zero_fill,
+                   int dtype, void* stream) {
+    if (!dst || !src || count < 0 || (dtype != 0 && dtype != 1)) return DD4ML_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (zero_fill) {
+        cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)n_dst * (dtype == 0 ? 4 : 8), s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    for (int base = 0; base < count; base += SEG_MAX) {
+        SegTable tb;
+        tb.count = (count - base < SEG_MAX) ? count - base : SEG_MAX;
+        int64_t maxlen = 1;
+        for (int i = 0; i < tb.count; ++i) {
+            tb.dst_off[i] = dst_off[base + i];
+            tb.src_off[i] = src_off[base + i];
+            tb.len[i] = lens[base + i];
+            if (tb.len[i] > maxlen) maxlen = tb.len[i];
+        }
+        int gx = (int)((maxlen + BLOCK * 8 - 1) / (BLOCK * 8));
+        if (gx < 1) gx = 1;
+        if (gx > 64) gx = 64;
+        dim3 grid(gx, tb.count);
+        if (dtype == 0) seg_copy_kernel<float><<<grid, BLOCK, 0, s>>>((float*)dst, (const float*)src, tb);
+        else seg_copy_kernel<double><<<grid, BLOCK, 0, s>>>((double*)dst, (const double*)src, tb);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -215,6 +215,15 @@ struct Compact {
     double G[M * M];     // Psi^T Psi
 };
 
+// Work arrays of the k-space routines.  On the device this lives in shared memory of
+// the last CTA (keeps the per-thread stack frame of the streaming kernels small).
+struct Scratch {
+    Compact C;
+    double R[M * M], LU[M * M], MR[M * M], RMR[M * M], U[M * M], RinvU[M * M], W[M * M];
+    double D[M], b[M], x[M], y[M], q[M], wv[M], col[M];
+    int piv[M], pw[M];
+};
+
 KS_FN inline void build_compact(const dd4ml_state* st, Compact& c) {
     const int k = (int)st->k[0];
     const double gam = st->gamma[0];
@@ -273,7 +282,7 @@ KS_FN inline double step_gp(const Compact& C, const double* b, double gg, const 
 // state; writes the step descriptor (cg, cS, cY) and the report fields.
 // =================================================================================
 template <class T>
-KS_FN inline void tr_solve(dd4ml_state* st, int mode) {
+KS_FN inline void tr_solve(dd4ml_state* st, int mode, Scratch* ws) {
     const double delta = st->delta[0], tol = st->tol[0], gg = st->gg[0];
     const int k = (st->second_order[0] != 0.0) ? (int)st->k[0] : 0;
     for (int i = 0; i < MS; ++i) { st->cS[i] = 0.0; st->cY[i] = 0.0; }
@@ -299,9 +308,9 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode) {
     }
 
     double pred, pp, gp;
-    Compact C;
+    Compact& C = ws->C;
     C.k = 0;
-    double b[M];
+    double* b = ws->b;
     StepK S;
     for (int i = 0; i < M; ++i) S.c[i] = 0.0;
 
@@ -326,13 +335,13 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode) {
         if (delta < 0) { st->err[0] = DD4ML_ERR_NEG_DELTA; st->solve_valid[0] = 0.0; return; }
 
         // ---- OBS (obs.py:61-95) ----
-        double R[M * M], LU[M * M], MR[M * M], RMR[M * M], U[M * M], D[M], RinvU[M * M];
-        int piv[M];
+        double *R = ws->R, *LU = ws->LU, *MR = ws->MR, *RMR = ws->RMR, *U = ws->U, *D = ws->D, *RinvU = ws->RinvU;
+        int* piv = ws->piv;
         if (!chol_upper(C.G, k, R)) { st->err[0] = DD4ML_ERR_CHOLESKY; st->solve_valid[0] = 0.0; return; }
         for (int i = 0; i < k * M; ++i) LU[i] = C.Minv[i];
         if (!lu_factor(LU, k, piv)) { st->err[0] = DD4ML_ERR_SINGULAR; st->solve_valid[0] = 0.0; return; }
         for (int c = 0; c < k; ++c) {  // MR[:, c] = Minv \ R^T[:, c]
-            double col[M];
+            double* col = ws->col;
             for (int r = 0; r < k; ++r) col[r] = R[c * M + r];
             lu_solve(LU, piv, k, col);
             for (int r = 0; r < k; ++r) MR[r * M + c] = col[r];
@@ -406,9 +415,9 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode) {
         const double tau = (double)tauT;
         st->tau[0] = tau;
         // SMW step exactly as coded (obs.py:175-182): p = -g/tau + Psi (tau Minv + G)^{-1} Psi^T g
-        double W[M * M], wv[M];
+        double *W = ws->W, *wv = ws->wv;
         for (int i = 0; i < k * M; ++i) W[i] = tau * C.Minv[i] + C.G[i];
-        int pw[M];
+        int* pw = ws->pw;
         if (!lu_factor(W, k, pw)) { st->err[0] = DD4ML_ERR_SINGULAR; st->solve_valid[0] = 0.0; return; }
         for (int i = 0; i < k; ++i) wv[i] = b[i];
         lu_solve(W, pw, k, wv);
@@ -417,7 +426,7 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode) {
         for (int i = 0; i < M; ++i) Pb.c[i] = (i < k) ? wv[i] : 0.0;
 
         // ---- Cauchy point and dogleg (optimizer_utils.py:259-296) ----
-        double x[M];
+        double* x = ws->x;
         for (int i = 0; i < k; ++i) x[i] = b[i];
         lu_solve(LU, piv, k, x);
         const double gBg = gam * gg + dotk(b, x, k);
@@ -456,13 +465,12 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode) {
         // ---- predicted reduction -(g^T p + 1/2 p^T B p) (optimizer_utils.py:298-305) ----
         pp = step_pp(C, b, gg, S);
         gp = step_gp(C, b, gg, S);
-        double q[M];
+        double *q = ws->q, *y = ws->y;
         for (int i = 0; i < k; ++i) {
             double s = S.cg * b[i];
             for (int j = 0; j < k; ++j) s += C.G[i * M + j] * S.c[j];
             q[i] = s;
         }
-        double y[M];
         for (int i = 0; i < k; ++i) y[i] = q[i];
         lu_solve(LU, piv, k, y);
         const double pBp = gam * pp + dotk(q, y, k);
@@ -507,7 +515,7 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode) {
 // joins the ring (dropping the oldest pair at capacity), the Gram blocks grow by one
 // row/column and gamma <- max(y^T y / y^T s, tol).
 // =================================================================================
-KS_FN inline bool lsr1_try_update(dd4ml_state* st) {
+KS_FN inline bool lsr1_try_update(dd4ml_state* st, Scratch* ws) {
     const double tol = st->tol[0];
     const double ss = st->c_ss[0], sy = st->c_sy[0], yy = st->c_yy[0];
     const int k = (int)st->k[0], m = (int)st->mem_len[0];
@@ -521,10 +529,10 @@ KS_FN inline bool lsr1_try_update(dd4ml_state* st) {
         us = sy - gam * ss;
         uu = yy - 2.0 * gam * sy + gam * gam * ss;
     } else {
-        Compact C;
+        Compact& C = ws->C;
         build_compact(st, C);
-        double bs[M], by[M], x[M], LU[M * M];
-        int piv[M];
+        double *bs = ws->b, *by = ws->y, *x = ws->x, *LU = ws->LU;
+        int* piv = ws->piv;
         for (int i = 0; i < k; ++i) {
             const int pi = (int)st->order[i];
             bs[i] = st->c_Ys[pi] - gam * st->c_Ss[pi];   // Psi^T s
@@ -581,6 +589,34 @@ KS_FN inline bool lsr1_try_update(dd4ml_state* st) {
     return true;
 }
 
+// LSR1.B (lsr1.py:181-198): out = gamma v + Psi (Minv \ Psi^T v), expressed as the
+// coefficients (cg, cS, cY) of the output pass.  S^T v, Y^T v are read from Sg, Yg.
+KS_FN inline void lsr1_B_coefs(dd4ml_state* st, Scratch* ws) {
+    const int k = (int)st->k[0];
+    const double gam = st->gamma[0];
+    for (int i = 0; i < MS; ++i) { st->cS[i] = 0.0; st->cY[i] = 0.0; }
+    st->cg[0] = gam;
+    st->converged[0] = 0.0;
+    st->solve_valid[0] = 0.0;
+    st->err[0] = DD4ML_ERR_NONE;
+    if (k == 0) return;
+    Compact& C = ws->C;
+    build_compact(st, C);
+    double* x = ws->x;
+    for (int i = 0; i < k; ++i) {
+        const int pi = (int)st->order[i];
+        x[i] = st->Yg[pi] - gam * st->Sg[pi];
+    }
+    for (int i = 0; i < k * M; ++i) ws->LU[i] = C.Minv[i];
+    if (!lu_factor(ws->LU, k, ws->piv)) { st->err[0] = DD4ML_ERR_SINGULAR; return; }
+    lu_solve(ws->LU, ws->piv, k, x);
+    for (int i = 0; i < k; ++i) {
+        const int pi = (int)st->order[i];
+        st->cY[pi] = x[i];
+        st->cS[pi] = -gam * x[i];
+    }
+}
+
 // rho and the accept decision of TR.step (tr.py:186-191), in the loss dtype T.
 template <class T>
 KS_FN inline bool tr_accept(double loss, double trial, double pred, double tol, double nu_dec, double* rho_out) {
@@ -597,7 +633,7 @@ KS_FN inline bool tr_accept(double loss, double trial, double pred, double tol, 
 // `accept` was decided by tr_accept; on acceptance the candidate reductions c_* and
 // out_gg / out_ginf (norms of the trial gradient) have been filled by the kernel.
 template <class T>
-KS_FN inline void tr_finish(dd4ml_state* st, bool accept, double rho) {
+KS_FN inline void tr_finish(dd4ml_state* st, bool accept, double rho, Scratch* ws) {
     st->rho[0] = rho;
     st->accept[0] = accept ? 1.0 : 0.0;
     st->pair_tried[0] = 0.0;
@@ -609,7 +645,7 @@ KS_FN inline void tr_finish(dd4ml_state* st, bool accept, double rho) {
             const double tol = st->tol[0];
             if (sqrt(st->c_ss[0]) > tol && sqrt(st->c_yy[0]) > tol) {  // tr.py:202
                 st->pair_tried[0] = 1.0;
-                lsr1_try_update(st);
+                lsr1_try_update(st, ws);
             }
         }
         if ((T)rho > (T)st->nu_inc[0] && (T)st->pnorm[0] >= (T)(0.9 * delta)) {  // tr.py:207
@@ -628,6 +664,14 @@ KS_FN inline void tr_finish(dd4ml_state* st, bool accept, double rho) {
 
 // APTS_Base.control_step decision (apts_base.py:483-501): reject when pred < tol or
 // rho < nu_dec; enlarge when rho > nu_inc.  delta is the APTS-level radius.
+template <class T>
+KS_FN inline bool apts_accept(double f0, double ftrial, double pred, double tol, double nu_dec) {
+    double rho;
+    if (fabs((double)(T)pred) < tol) rho = INFINITY;
+    else rho = (double)(((T)f0 - (T)ftrial) / (T)pred);
+    return !((T)pred < (T)tol || (T)rho < (T)nu_dec);
+}
+
 template <class T>
 KS_FN inline bool apts_control(dd4ml_state* st, double f0, double ftrial, double pred) {
     const double tol = st->tol[0];

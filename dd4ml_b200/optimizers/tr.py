@@ -1,0 +1,247 @@
+"""Trust-region optimizer, drop-in for ``dd4ml.optimizers.tr.TR`` (tr.py:14-222).
+
+One TR iteration is three fused kernels around the (untouched, PyTorch) closure:
+
+    tr_propose   ||g||, S^T g, Y^T g in one read of (g, S, Y); the last CTA solves the
+                 sub-problem in k-space (first-order, or L-SR1 + OBS + optional dogleg)
+    tr_apply     p = cg g + sum_j (cS_j S_j + cY_j Y_j),  w += p        (one read, one write)
+    <closure>    trial loss / gradient (PyTorch forward + backward)
+    tr_decide    rho test on the device; accepted: y = g+ - g, every reduction of the
+                 L-SR1 update chain, g_out <- g+, ring/Gram/gamma/radius update in the
+                 last CTA; rejected: w -= p, radius shrink
+
+followed by ONE packed read of the report block (the reference takes >= 6 host syncs per
+step).  Parameters and gradients are views of flat buffers (flat.py), so
+``_flat_grad`` / ``_apply_update`` cost no per-tensor launches.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Tuple
+
+import torch
+from torch.optim import Optimizer
+
+from .. import _lib
+from .._device import DeviceState
+from ..flat import get_flat
+from ..utility.optimizer_utils import get_tr_hparams
+from .lsr1 import LSR1
+
+_HP = ("delta", "min_delta", "max_delta", "nu_dec", "nu_inc", "inc_factor", "dec_factor", "tol")
+
+
+def as_device_scalar(x, device, like_dtype=torch.float32) -> torch.Tensor:
+    """0-d contiguous CUDA fp32/fp64 tensor for a loss value (tensor, python float ...)."""
+    if torch.is_tensor(x):
+        t = x.detach()
+        if t.device != device or t.dtype not in (torch.float32, torch.float64):
+            t = t.to(device=device, dtype=like_dtype if t.dtype not in (torch.float32, torch.float64) else t.dtype)
+        return t.reshape(()).contiguous()
+    return torch.tensor(float(x), dtype=like_dtype, device=device)
+
+
+class TR(Optimizer):
+    __name__ = "TR"
+
+    @staticmethod
+    def setup_TR_hparams(cfg):
+        for k, v in get_tr_hparams(cfg).items():
+            setattr(cfg, k, v)
+        return cfg
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], *,
+                 flat_grads_fn: Callable[[], torch.Tensor] | None = None,
+                 flat_params_fn: Callable[[], torch.Tensor] | None = None, **kwargs) -> None:
+        self.delta = kwargs.pop("delta", 0.1)
+        self.norm_type = kwargs.pop("norm_type", 2)
+        self.tol = float(kwargs.pop("tol", 1e-6))
+        self.second_order = bool(kwargs.pop("second_order", False))
+        self.dogleg = bool(kwargs.pop("dogleg", False))
+        if self.dogleg and not self.second_order:
+            raise ValueError("Dogleg is only applicable in second-order mode")
+        self.mem_length = int(kwargs.pop("mem_length", 10))
+        self.nu_dec = kwargs.pop("nu_dec")
+        self.nu_inc = kwargs.pop("nu_inc")
+        self.max_delta = kwargs.pop("max_delta")
+        self.inc_factor = kwargs.pop("inc_factor")
+        self.min_delta = kwargs.pop("min_delta")
+        self.dec_factor = kwargs.pop("dec_factor")
+        if self.norm_type not in (2, 2.0, float("inf")):
+            raise _lib.DD4MLError("dd4ml_b200 TR supports norm_type 2 and inf")
+        self._flat_grads_fn = flat_grads_fn
+        self._flat_params_fn = flat_params_fn
+
+        super().__init__(params, {"lr": self.delta})
+        self.ps = [p for g in self.param_groups for p in g["params"]]
+        self.shapes = [p.shape for p in self.ps]
+        self.numels = [p.numel() for p in self.ps]
+        self._fs = get_flat(self.ps)
+        self._fs_version = self._fs.version
+        device = self._fs.device
+
+        if self.second_order:
+            # tr.py:76-78: gamma 1.0, fp32 pairs whatever the parameter dtype
+            self.hess = LSR1(gamma=1.0, memory_length=self.mem_length, device=device, tol=self.tol)
+            self._ds = self.hess.ds
+            from ..solvers.obs import OBS
+            self.obs = OBS()
+        else:
+            self.hess = None  # type: ignore
+            self.obs = None  # type: ignore
+            self._ds = DeviceState(device)
+        self._ds.set(norm_inf=1.0 if self.norm_type == float("inf") else 0.0,
+                     second_order=1.0 if self.second_order else 0.0,
+                     dogleg=1.0 if self.dogleg else 0.0, mem_len=self.mem_length)
+        self._pushed: dict[str, float] = {}
+        self._bufs: dict[torch.dtype, dict[str, torch.Tensor]] = {}
+        self._known_gn: tuple | None = None     # (id, _version, data_ptr, gn) of the last returned gradient
+        self._step_buf = None
+        self._step_norm_cache = None
+        self.last_report = None
+        self.last_grad_norm = None
+
+    # ------------------------------------------------------------------ plumbing
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """One memset of the flat gradient buffer; the views stay bound."""
+        self._fs.zero_grad()
+
+    def update_pytorch_lr(self) -> None:
+        for g in self.param_groups:
+            g["lr"] = self.delta
+
+    def _push_hparams(self):
+        cur = {k: float(getattr(self, k)) for k in _HP}
+        diff = {k: v for k, v in cur.items() if self._pushed.get(k) != v}
+        if diff:
+            self._ds.set(**diff)
+            self._pushed.update(diff)
+
+    def _buffers(self, dtype):
+        if self._fs.version != self._fs_version:
+            self._bufs.clear()
+            self._fs_version = self._fs.version
+        b = self._bufs.get(dtype)
+        if b is None:
+            n, dev = self._fs.n, self._fs.device
+            b = {k: torch.zeros(n, dtype=dtype, device=dev) for k in ("step", "g_out", "g_in")}
+            self._bufs[dtype] = b
+        return b
+
+    def _grad_dtype(self):
+        # tr.py:69: the gradient buffer is fp32 unless the flat_grads_fn hook supplies it
+        return torch.float32
+
+    def _current_grad(self, vt) -> torch.Tensor:
+        """Flat view of the gradient the last backward produced, in dtype vt."""
+        if self._flat_grads_fn is not None:
+            g = self._flat_grads_fn()
+            return g if g.dtype == vt else g.to(vt)
+        G = self._fs.flat_grad()
+        if G.dtype == vt:
+            return G
+        b = self._buffers(vt)
+        c = b.setdefault("g_cast", torch.empty_like(b["step"]))
+        c.copy_(G)
+        return c
+
+    def _flat_grad(self) -> torch.Tensor:
+        """tr.py:88-104: the current gradient as a fresh flat vector."""
+        if self._flat_grads_fn is not None:
+            return self._flat_grads_fn().clone()
+        b = self._buffers(torch.float32)
+        b["g_in"].copy_(self._fs.flat_grad())
+        return b["g_in"]
+
+    def _params_target(self):
+        """Flat parameter vector the kernels update in place."""
+        if self._flat_params_fn is not None:
+            return self._flat_params_fn().detach().clone()
+        self._fs.ensure()
+        return self._fs.data
+
+    def _apply_update(self, sign: float = 1.0) -> None:
+        """tr.py:106-131 (compatibility; the step path applies updates inside the kernels)."""
+        with torch.no_grad():
+            if self._flat_params_fn is not None:
+                updated = self._flat_params_fn() + sign * self._step_buf
+                torch.nn.utils.vector_to_parameters(updated, self.ps)
+            else:
+                self._fs.data.add_(self._step_buf.to(self._fs.dtype), alpha=sign)
+
+    # ------------------------------------------------------------------ the step
+    def step(self, closure, **_) -> Tuple[torch.Tensor, torch.Tensor]:
+        lib, ds = self._ds.lib, self._ds
+        dev = self._fs.device
+        loss = _["loss"] if "loss" in _ else closure(compute_grad=True)
+        grad = _["grad"] if "grad" in _ else self._flat_grad()
+        grad = grad.detach()
+        if not grad.is_contiguous():
+            grad = grad.contiguous()
+        vt = grad.dtype
+        n = grad.numel()
+        if n != self._fs.n:
+            raise _lib.DD4MLError(f"dd4ml_b200 TR: gradient has {n} elements, parameters {self._fs.n}")
+        w = self._params_target()
+        b = self._buffers(vt)
+        self._push_hparams()
+        loss_t = as_device_scalar(loss, dev)
+        st = _lib.stream()
+        h = self.hess
+        if h is not None:
+            h.ensure_storage(n)
+            S, Y, ld, ht = h.S_ptr, h.Y_ptr, h.ld, _lib.dt(h.dtype)
+        else:
+            S = Y = None
+            ld, ht = n, _lib.F32
+        vtc, wtc = _lib.dt(vt), _lib.dt(w.dtype)
+
+        lib.tr_propose(ds.sp, ds.wp, _lib.ptr(grad), S, Y, n, ld, vtc, ht, 0, st)
+        # convergence test (tr.py:147): ||g|| is already known on the host when `grad` is the
+        # vector this optimizer returned last time; otherwise one extra report read.
+        kg = self._known_gn
+        if kg is not None and kg[0] == id(grad) and kg[1] == grad._version and kg[2] == grad.data_ptr():
+            gn = kg[3]
+        else:
+            rep = ds.read()
+            DeviceState.raise_for(rep.err)
+            gn = rep.gn
+        if gn <= self.tol:
+            self.last_grad_norm = gn
+            return loss, grad
+
+        self._step_buf = b["step"]
+        lib.tr_apply(ds.sp, ds.wp, _lib.ptr(grad), S, Y, _lib.ptr(self._step_buf), _lib.ptr(w), n, ld,
+                     vtc, ht, wtc, st)
+        if self._flat_params_fn is not None:
+            torch.nn.utils.vector_to_parameters(w, self.ps)
+        trial_loss = closure(compute_grad=True)
+        trial_t = as_device_scalar(trial_loss, dev, loss_t.dtype)
+        if trial_t.dtype != loss_t.dtype:
+            trial_t = trial_t.to(loss_t.dtype)
+        G = self._current_grad(vt)
+        g_out = b["g_out"]
+        lib.tr_decide(ds.sp, ds.wp, _lib.ptr(loss_t), _lib.ptr(trial_t), _lib.dt(loss_t.dtype), _lib.ptr(G),
+                      _lib.ptr(grad), _lib.ptr(g_out), _lib.ptr(self._step_buf), _lib.ptr(w), S, Y, n, ld,
+                      vtc, ht, wtc, st)
+        rep = ds.read()
+        DeviceState.raise_for(rep.err)
+        self.last_report = rep
+        self.delta = rep.delta
+        self._pushed["delta"] = float(rep.delta)
+        self._step_norm_cache = rep.pnorm
+        if h is not None:
+            h.absorb(rep)
+        self.update_pytorch_lr()
+        accepted = rep.accept != 0.0
+        if self._flat_params_fn is not None and not accepted:
+            torch.nn.utils.vector_to_parameters(w, self.ps)
+        out_loss, out_grad = (trial_loss, g_out) if accepted else (loss, grad)
+        self._known_gn = (id(out_grad), out_grad._version, out_grad.data_ptr(), rep.out_gn)
+        self.last_grad_norm = rep.out_gn
+        return out_loss, out_grad
+
+    # ------------------------------------------------------------------ checkpointing
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["dd4ml_b200"] = {"delta": self.delta, "hess": None if self.hess is None else self.hess.state_dict()}
+        return sd

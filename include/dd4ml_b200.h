@@ -1,0 +1,131 @@
+/* dd4ml_b200 -- C ABI of the B200-native trust-region hot path of cruzas/DD4ML.
+ *
+ * The reference is pure Python/PyTorch, so there is no FFI to replace; each entry
+ * point below is the fused device-side replacement of the ATen op sequence of one
+ * reference function on the hot path (file:line cited per function, paths relative
+ * to the reference's src/dd4ml/).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer borrowed from
+ *     the caller (PyTorch storages); the library allocates nothing.
+ *   - dtype codes: 0 = float32, 1 = float64.  vt = dtype of gradient/step vectors,
+ *     ht = dtype of the L-SR1 pairs, wt = dtype of the parameters, lt = dtype of the
+ *     0-d loss tensors.  Supported (ht,vt,wt): (0,0,0) (0,0,1) (0,1,1) (1,1,1).
+ *   - `state`  : device block of dd4ml_state_doubles() doubles (csrc/state.h), one per
+ *     optimizer instance.  `ws`: device workspace of dd4ml_workspace_doubles() doubles.
+ *   - S, Y     : L-SR1 pair-major ring buffers, DD4ML_MAXS slots of `ld` elements
+ *     (ld >= n, ld % 4 == 0), slot j at S + j*ld.
+ *   - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises.
+ *   - return value: 0 on success, otherwise a cudaError_t or a DD4ML_E_* code
+ *     (dd4ml_error_string).  Numerical failures (Cholesky, singular solve, NaN) are
+ *     reported through state.err, read by the host with the report block.
+ */
+#ifndef DD4ML_B200_H
+#define DD4ML_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD4ML_E_DTYPE 10001      /* unsupported dtype combination */
+#define DD4ML_E_ARG 10002        /* bad argument (n < 0, ld, null pointer, mem_length > DD4ML_MAXM) */
+#define DD4ML_E_ALIGN 10003      /* reserved */
+
+int dd4ml_version(void);
+const char* dd4ml_error_string(int code);
+
+/* layout of the state block (name/offset/count in doubles) and sizes */
+int dd4ml_state_doubles(void);
+int dd4ml_workspace_doubles(void);
+int dd4ml_num_fields(void);
+int dd4ml_field(int i, const char** name, int* offset, int* count);
+int dd4ml_max_mem_length(void);
+
+/* zero the state + workspace and install defaults (gamma, spare slot) */
+int dd4ml_state_init(double* state, double* ws, double gamma0, void* stream);
+/* state[offsets[i]] = values[i], i < count <= 32 (hyper-parameters, delta written by the host) */
+int dd4ml_state_set(double* state, int count, const int* offsets, const double* values, void* stream);
+
+/* ---- TR.step, optimizers/tr.py:138-222 -------------------------------------------------
+ * propose: ||g|| (2 or inf), S^T g, Y^T g in one pass; the last CTA then solves the
+ *   sub-problem in k-space (utility/optimizer_utils.py:197-307, optimizers/lsr1.py:146-198,
+ *   solvers/obs.py:46-254) and leaves the step descriptor in `state`.
+ *   mode 0 = TR, 1 = LSSR1_TR (clip + descent flip, lssr1_tr.py:563-587).
+ * apply:   p = cg*g + sum_j cS_j S_j + cY_j Y_j;  optionally w += p  (tr.py:106-131,179).
+ * decide:  rho test (tr.py:186-191); accepted: y = g_trial - g_old, candidate pair
+ *   reductions, g_out <- g_trial, L-SR1 update chain + radius update in the last CTA
+ *   (lsr1.py:53-144, tr.py:193-214); rejected: w -= p, radius shrink (tr.py:216-222). */
+int dd4ml_tr_propose(double* state, double* ws, const void* g, const void* S, const void* Y,
+                     int64_t n, int64_t ld, int vt, int ht, int mode, void* stream);
+int dd4ml_tr_apply(double* state, double* ws, const void* g, const void* S, const void* Y, void* p,
+                   void* w, int64_t n, int64_t ld, int vt, int ht, int wt, void* stream);
+int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* trial_loss, int lt,
+                    const void* g_trial, const void* g_old, void* g_out, const void* p, void* w,
+                    void* S, void* Y, int64_t n, int64_t ld, int vt, int ht, int wt, void* stream);
+
+/* ---- LSSR1_TR.step, optimizers/lssr1_tr.py:493-654 --------------------------------------
+ * begin: s = w - old_w, y = g - prev_g (lssr1_tr.py:518-526) with every reduction of the
+ *   L-SR1 update chain and of the sub-problem in one pass; old_w <- w, prev_g <- g; the last
+ *   CTA runs update_memory, precompute and the sub-problem solve; `loss` (phi_0) is copied into
+ *   the report block so the host needs no separate read.
+ * trial: w = base + alpha * p (lssr1_tr.py:262).
+ * eval:  deriv = g . p, g_save <- g, loss copied into the report (lssr1_tr.py:265-271). */
+int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void* old_w, const void* g,
+                      void* prev_g, int has_prev, void* S, void* Y, const void* loss, int lt,
+                      int64_t n, int64_t ld, int vt, int ht, int wt, void* stream);
+int dd4ml_lssr1_trial(void* w, const void* base, const void* p, double alpha, int64_t n, int vt,
+                      int wt, void* stream);
+int dd4ml_lssr1_eval(double* state, double* ws, const void* g, const void* p, void* g_save,
+                     const void* loss, int lt, int64_t n, int vt, void* stream);
+
+/* ---- APTS, optimizers/apts_base.py / apts_d.py / apts_p.py -------------------------------
+ * residual: g0 <- Gg, gl0 <- Gl, resid <- Gg - Gl  (apts_d.py:179-186).
+ * foc:      loss_out = loss_in + resid.(w_loc - w_glob) if ||w_loc - w_glob|| > tol
+ *           (apts_base.py:262-292).
+ * pack:     buf[0:n] = w_loc - w0, buf[n] = (loss0 - loss1)*weight, buf[n+1] = evals
+ *           (apts_d.py:195-196,139-141; apts_base.py:411-416) -- the all-reduce payload.
+ * trial:    mode 0: w = w0 + buf*scale (apts_base.py:445, apts_d.py:149-150);
+ *           mode 1: w = w0 + clamp(buf - w0, -clampv, clampv) (apts_p.py:221-224).
+ * control:  APTS_Base.control_step decision (apts_base.py:483-501): accepted: g0 <- G
+ *           (trial gradient), loss_out <- f_trial; rejected: w <- w0, loss_out <- f0;
+ *           radius update on `state`; `aux` (nullable, dtype pt) is copied into state.aux so the
+ *           summed evaluation counter of the same all-reduce rides along with the report. */
+int dd4ml_apts_residual(const void* Gg, const void* Gl, void* g0, void* gl0, void* resid,
+                        int64_t n, int vt, void* stream);
+int dd4ml_apts_foc(double* state, double* ws, const void* w_loc, const void* w_glob,
+                   const void* resid, const void* loss_in, void* loss_out, int lt, double tol,
+                   int64_t n, int vt, int wt, void* stream);
+int dd4ml_apts_pack(void* buf, const void* w_loc, const void* w0, const void* loss0,
+                    const void* loss1, int lt, double weight, double evals, int64_t n, int wt,
+                    void* stream);
+int dd4ml_apts_trial(void* w, const void* w0, const void* buf, int mode, double scale,
+                     double clampv, int64_t n, int wt, void* stream);
+int dd4ml_apts_control(double* state, double* ws, const void* f0, const void* ftrial, int lt,
+                       const void* pred, int pt, void* w, const void* w0, void* g0, const void* G,
+                       void* loss_out, const void* aux, int64_t n, int vt, int wt, void* stream);
+
+/* ---- flat-buffer plumbing (utility/apts_utils.py:17-62, tr.py:88-104) ---------------------
+ * gather:   dst[off_i : off_i+len_i] = src_i  for up to 96 tensors per call (multi-tensor).
+ * seg_copy: dst[dst_off_i : +len_i] = src[src_off_i : +len_i]; optional zero fill of dst
+ *           first (apts_p.py:145-150). */
+int dd4ml_gather(void* dst, int count, const void* const* srcs, const int64_t* offsets,
+                 const int64_t* lens, int dtype, void* stream);
+int dd4ml_seg_copy(void* dst, const void* src, int count, const int64_t* dst_off,
+                   const int64_t* src_off, const int64_t* lens, int64_t n_dst, int zero_fill,
+                   int dtype, void* stream);
+
+/* ---- LSR1.update_memory, optimizers/lsr1.py:53-144: candidate reductions in one pass (the
+ * pair is written to the spare ring slot), acceptance chain + Gram/gamma update in the last CTA */
+int dd4ml_lsr1_update(double* state, double* ws, const void* s, const void* y, void* S, void* Y,
+                      int64_t n, int64_t ld, int vt, int ht, void* stream);
+
+/* ---- LSR1.B, optimizers/lsr1.py:181-198: out = gamma v + Psi (Minv \ Psi^T v) -------------
+ * two launches: reduce (S^T v, Y^T v) + k-space solve in the last CTA, then the output pass. */
+int dd4ml_lsr1_B(double* state, double* ws, const void* v, const void* S, const void* Y, void* out,
+                 int64_t n, int64_t ld, int vt, int ht, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

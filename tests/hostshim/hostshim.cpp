@@ -15,16 +15,18 @@ int hostshim_field(int i, const char** name, int* offset, int* count) {
     return 0;
 }
 void hostshim_tr_solve(double* st, int mode, int is_float) {
-    if (is_float) ks::tr_solve<float>((dd4ml_state*)st, mode);
-    else ks::tr_solve<double>((dd4ml_state*)st, mode);
+    ks::Scratch ws;
+    if (is_float) ks::tr_solve<float>((dd4ml_state*)st, mode, &ws);
+    else ks::tr_solve<double>((dd4ml_state*)st, mode, &ws);
 }
-int hostshim_try_update(double* st) { return ks::lsr1_try_update((dd4ml_state*)st) ? 1 : 0; }
+int hostshim_try_update(double* st) { ks::Scratch ws; return ks::lsr1_try_update((dd4ml_state*)st, &ws) ? 1 : 0; }
 void hostshim_tr_finish(double* st, double loss, double trial, int is_float) {
     dd4ml_state* s = (dd4ml_state*)st;
     double rho;
     bool acc = is_float ? ks::tr_accept<float>(loss, trial, s->pred[0], s->tol[0], s->nu_dec[0], &rho)
                         : ks::tr_accept<double>(loss, trial, s->pred[0], s->tol[0], s->nu_dec[0], &rho);
-    if (is_float) ks::tr_finish<float>(s, acc, rho); else ks::tr_finish<double>(s, acc, rho);
+    ks::Scratch ws;
+    if (is_float) ks::tr_finish<float>(s, acc, rho, &ws); else ks::tr_finish<double>(s, acc, rho, &ws);
 }
 int hostshim_apts_control(double* st, double f0, double ft, double pred, int is_float) {
     return (is_float ? ks::apts_control<float>((dd4ml_state*)st, f0, ft, pred)

@@ -1,0 +1,70 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dd4ml_b200.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "dd4ml_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dd4ml_[a-zA-Z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from dd4ml_b200 import _lib
+    lib = _lib.get()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib.cdll, n), f"{n} declared in include/dd4ml_b200.h but not exported"
+    assert set(_lib.EXPORTS) <= set(names)
+    assert lib.cdll.dd4ml_version() >= 100
+
+
+def test_state_layout_is_consistent():
+    from dd4ml_b200 import _lib
+    lay = _lib.get().layout
+    assert lay.size == _lib.get().state_doubles
+    assert lay.report_end < lay.size
+    offs = sorted((o, c) for o, c in lay.fields.values())
+    for (o, c), (o2, _) in zip(offs, offs[1:]):
+        assert o + c == o2
+    assert lay.maxs == lay.maxm + 1
+
+
+def test_no_cpu_path():
+    import pytest
+    import torch
+    import dd4ml_b200
+    from dd4ml_b200.utility.optimizer_utils import get_tr_hparams
+    from dd4ml_b200.workloads import Cfg
+    m = torch.nn.Linear(3, 2)
+    hp = get_tr_hparams(Cfg(delta=0.1, min_delta=1e-3, max_delta=2.0, norm_type=2, glob_second_order=False,
+                            glob_dogleg=False, tol=1e-6))
+    with pytest.raises(dd4ml_b200.DD4MLError):
+        dd4ml_b200.TR(m.parameters(), **hp)
+    with pytest.raises(dd4ml_b200.DD4MLError):
+        dd4ml_b200.LSR1(device="cpu")
+
+
+def test_hparam_tables_match_reference_values():
+    """optimizer_utils.py:27-151 constants."""
+    import math
+    from dd4ml_b200.utility.optimizer_utils import (get_apts_hparams, get_loc_tr_hparams, get_lssr1_loc_tr_hparams,
+                                                    get_lssr1_tr_hparams, get_tr_hparams)
+    from dd4ml_b200.workloads import apts_d_yaml_config
+    c = apts_d_yaml_config()
+    a = get_apts_hparams(c)
+    assert (a["nu_dec"], a["nu_inc"], a["inc_factor"], a["dec_factor"]) == (0.25, 0.75, 1.2, 0.9)
+    t = get_tr_hparams(c)
+    assert t["mem_length"] == 5 and t["nu_dec"] == 0.25 and t["inc_factor"] == 1.2 and t["second_order"] is True
+    lt = get_loc_tr_hparams(c)
+    assert (lt["nu_dec"], lt["nu_inc"], lt["inc_factor"], lt["dec_factor"]) == (0.3, 0.7, 1.5, 0.6)
+    g = get_lssr1_tr_hparams(c)
+    assert g["gamma"] == 1e-3 and g["alpha_max"] == 2.0 and g["sync"] is True and g["nu_3"] == 0.9 and g["c_2"] == 0.9
+    l = get_lssr1_loc_tr_hparams(c)
+    assert l["sync"] is False and l["delta"] == c.delta
+    c.norm_type = math.inf
+    assert get_loc_tr_hparams(c)["delta"] == c.delta

@@ -1,0 +1,287 @@
+"""GPU parity tests of the drop-in optimizer classes against the CPU oracle (same seeded
+inputs) and against goldens from the unmodified reference.
+
+Tolerances.  Per-step vectors: 1e-5 relative (north star, fp32) wherever the step does not
+depend on LAPACK's eigenvector signs.  Loss trajectories: the model
+forward/backward runs on the GPU here and on the CPU in the oracle/reference, so
+trajectories drift by rounding; stated bounds per test.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from _helpers import FFNN, load_golden, make_fg, rel_err, set_flat, sine_crit
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import dd4ml_b200
+    from dd4ml_b200 import APTS_D, APTS_P, LSSR1_TR, TR
+    from dd4ml_b200.utility.optimizer_utils import (get_loc_tr_hparams, get_lssr1_loc_tr_hparams,
+                                                    get_lssr1_tr_hparams, get_tr_hparams)
+
+import oracle
+
+DEV = "cuda"
+IN_F, HID, OUT = 36, [12, 12], 10
+
+
+class Cfg:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def cfg(**kw):
+    base = dict(delta=0.1, min_delta=0.01, max_delta=1.0, norm_type=2, glob_second_order=False,
+                glob_dogleg=False, loc_second_order=False, loc_dogleg=False, mem_length=3,
+                max_wolfe_iters=5, max_zoom_iters=5, tol=1e-6, paper_tr_update=False)
+    base.update(kw)
+    return Cfg(**base)
+
+
+def gpu_model(g, dtype=torch.float32, hidden=HID, in_f=IN_F, out_f=OUT, log_softmax=True):
+    m = FFNN(in_f, hidden, out_f, log_softmax).to(dtype)
+    set_flat(m, torch.from_numpy(g["w0"]).to(dtype))
+    return m.to(DEV)
+
+
+def flat_of(model):
+    return torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu()
+
+
+def make_closure(opt, model, X, Y, crit=None):
+    crit = crit or nn.CrossEntropyLoss()
+
+    def closure(compute_grad=True):
+        opt.zero_grad()
+        loss = crit(model(X), Y)
+        if compute_grad:
+            loss.backward()
+        return loss
+    return closure
+
+
+# ------------------------------------------------------------------------------ plain TR
+@pytest.mark.parametrize("name,so,dog,norm", [
+    ("tr_fo", False, False, 2), ("tr_fo_inf", False, False, math.inf),
+    ("tr_so", True, False, 2), ("tr_so_dogleg", True, True, 2)])
+def test_tr_matches_oracle_and_reference(name, so, dog, norm):
+    g = load_golden(name)
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    model = gpu_model(g)
+    hp = get_tr_hparams(cfg(delta=0.1, min_delta=1e-3, max_delta=2.0, norm_type=norm,
+                            glob_second_order=so, glob_dogleg=dog))
+    opt = TR(model.parameters(), **hp)
+    closure = make_closure(opt, model, X.to(DEV), Y.to(DEV))
+    # oracle on the same inputs (CPU), this implementation's eigenvector sign convention
+    ohp = oracle.tr_hparams(0.1, 1e-3, 2.0, norm_type=norm, second_order=so, dogleg=dog)
+    oopt = oracle.TROracle(**ohp, eig_sign="canonical")
+    ofg = make_fg(FFNN(IN_F, HID, OUT), X, Y)
+    ow = torch.from_numpy(g["w0"]).clone()
+    steps = int(g["steps"])
+    losses, deltas, olosses = [], [], []
+    first_div = None
+    for i in range(steps):
+        w_before = flat_of(model)
+        loss, grad = opt.step(closure)
+        oloss, _ = oopt.step(ofg, ow)
+        losses.append(float(loss)); deltas.append(float(opt.delta)); olosses.append(float(oloss))
+        if first_div is None and (abs(deltas[-1] - oopt.delta) > 1e-9 or rel_err(flat_of(model), ow) > 1e-3):
+            first_div = i
+        if i == 0:      # per-step vector parity on identical inputs
+            assert rel_err(flat_of(model) - w_before, torch.from_numpy(g["w_step1"]) - torch.from_numpy(g["w0"])) < 1e-5
+    print(f"{name}: first divergence from the oracle at step {first_div}; final loss {losses[-1]:.6f} "
+          f"oracle {olosses[-1]:.6f} reference {float(g['loss'][-1]):.6f}")
+    if not so:
+        # first-order: no eigen-solver involved -> the whole trajectory matches the reference
+        np.testing.assert_allclose(losses, g["loss"], rtol=2e-4)
+        np.testing.assert_allclose(deltas, g["delta"], rtol=1e-9)
+        assert rel_err(flat_of(model), g["w_final"]) < 2e-3
+    else:
+        # second order: identical until a borderline accept/reject or a sign-sensitive OBS start
+        k = 10
+        np.testing.assert_allclose(losses[:k], olosses[:k], rtol=5e-4)
+        assert first_div is None or first_div >= 5
+        assert losses[-1] < losses[0]
+
+
+def test_tr_converged_gradient_returns_immediately():
+    model = nn.Linear(4, 1).to(DEV)
+    opt = TR(model.parameters(), **get_tr_hparams(cfg()))
+    calls = []
+
+    def closure(compute_grad=True):
+        opt.zero_grad()
+        calls.append(1)
+        loss = (model.weight * 0).sum() + (model.bias * 0).sum() + 1.0
+        loss.backward()
+        return loss
+    loss, grad = opt.step(closure)
+    assert len(calls) == 1 and float(loss) == 1.0 and float(grad.abs().max()) == 0.0
+
+
+def test_tr_rejects_and_restores_parameters():
+    torch.manual_seed(0)
+    model = nn.Linear(8, 1, bias=False).to(DEV)
+    w0 = model.weight.detach().clone()
+    opt = TR(model.parameters(), **get_tr_hparams(cfg(delta=0.5, min_delta=1e-3, max_delta=2.0)))
+    n_call = [0]
+
+    def closure(compute_grad=True):     # the trial point is made to look worse
+        opt.zero_grad()
+        n_call[0] += 1
+        loss = (model.weight ** 2).sum() * (1.0 if n_call[0] == 1 else -1.0) + (10.0 if n_call[0] > 1 else 0.0)
+        loss.backward()
+        return loss
+    loss, grad = opt.step(closure)
+    assert opt.last_report.accept == 0.0
+    assert opt.delta == pytest.approx(0.45)
+    assert torch.allclose(model.weight, w0, atol=1e-6)
+
+
+def test_flat_views_survive_set_to_none():
+    g = load_golden("tr_fo")
+    X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
+    model = gpu_model(g)
+    opt = TR(model.parameters(), **get_tr_hparams(cfg(delta=0.1, min_delta=1e-3, max_delta=2.0)))
+    crit = nn.CrossEntropyLoss()
+
+    def closure(compute_grad=True):      # the reference Trainer's closure: model.zero_grad() -> grads become None
+        model.zero_grad(set_to_none=True)
+        loss = crit(model(X), Y)
+        loss.backward()
+        return loss
+    losses = [float(opt.step(closure)[0]) for _ in range(5)]
+    np.testing.assert_allclose(losses, g["loss"][:5], rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------ LSSR1_TR
+@pytest.mark.parametrize("name,kw", [
+    ("lssr1_fo", dict(glob_second_order=False)),
+    ("lssr1_so_dog0", dict(glob_second_order=True, glob_dogleg=False)),
+    ("lssr1_so_dog1", dict(glob_second_order=True, glob_dogleg=True)),
+    ("lssr1_paper", dict(glob_second_order=True, paper_tr_update=True))])
+def test_lssr1_matches_oracle_and_reference(name, kw):
+    g = load_golden(name)
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    model = gpu_model(g)
+    hp = get_lssr1_tr_hparams(cfg(**kw))
+    hp["sync"] = False
+    opt = LSSR1_TR(model.parameters(), **hp)
+    closure = make_closure(opt, model, X.to(DEV), Y.to(DEV))
+    ohp = oracle.lssr1_hparams(0.1, 0.01, 1.0, mem_length=3, second_order=kw.get("glob_second_order", True),
+                               dogleg=kw.get("glob_dogleg", False), paper_tr_update=kw.get("paper_tr_update", False))
+    ohp.pop("sync")
+    oopt = oracle.LSSR1TROracle(**ohp, eig_sign="canonical")
+    ofg = make_fg(FFNN(IN_F, HID, OUT), X, Y)
+    ow = torch.from_numpy(g["w0"]).clone()
+    losses, olosses, deltas = [], [], []
+    first_div = None
+    for i in range(int(g["steps"])):
+        loss, _ = opt.step(closure)
+        oloss, _ = oopt.step(ofg, ow)
+        losses.append(float(loss)); olosses.append(float(oloss)); deltas.append(float(opt.delta))
+        if first_div is None and (abs(deltas[-1] - oopt.delta) > 1e-9 or rel_err(flat_of(model), ow) > 1e-3):
+            first_div = i
+    print(f"{name}: first divergence from the oracle at step {first_div}; final loss {losses[-1]:.6f} "
+          f"oracle {olosses[-1]:.6f} reference {float(g['loss'][-1]):.6f}")
+    if name == "lssr1_fo":
+        np.testing.assert_allclose(losses, g["loss"], rtol=2e-4)
+        np.testing.assert_allclose(deltas, g["delta"], rtol=1e-9)
+    else:
+        k = 6
+        np.testing.assert_allclose(losses[:k], olosses[:k], rtol=5e-4)
+        np.testing.assert_allclose(losses[:4], g["loss"][:4], rtol=5e-4)
+        assert losses[-1] < losses[0]
+
+
+# ------------------------------------------------------------------------------ APTS (single rank)
+def _apts(kind, model, glob, loc, c, **extra):
+    cls = APTS_D if kind == "d" else APTS_P
+    c.glob_opt, c.loc_opt = glob, loc
+    c = cls.setup_APTS_hparams(c)
+    return cls(model.parameters(), model=model, criterion=nn.CrossEntropyLoss(), device=DEV, nr_models=1,
+               glob_opt=c.glob_opt, glob_opt_hparams=c.glob_opt_hparams, loc_opt=c.loc_opt,
+               loc_opt_hparams=c.loc_opt_hparams, glob_pass=True, norm_type=c.norm_type, max_loc_iters=3,
+               max_glob_iters=1, tol=1e-6, **extra, **c.apts_params)
+
+
+def test_apts_d_single_rank_matches_reference():
+    g = load_golden("apts_d_tr_fo_ws1")
+    X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
+    model = gpu_model(g)
+    opt = _apts("d", model, "tr", "tr", cfg(), foc=True)
+    losses, deltas, gev = [], [], []
+    for i in range(int(g["steps"])):
+        losses.append(float(opt.step(X, Y)))
+        deltas.append(float(opt.delta)); gev.append(opt.grad_evals)
+        if i == 0:
+            assert rel_err(flat_of(model), g["w_step1"]) < 1e-5
+    np.testing.assert_allclose(losses, g["loss"], rtol=5e-4)
+    np.testing.assert_allclose(deltas, g["delta"], rtol=1e-9)
+    np.testing.assert_allclose(gev, g["grad_evals"], atol=1e-9)
+    assert rel_err(flat_of(model), g["w_final"]) < 5e-3
+    # local clone equals the global model after the sync
+    assert torch.equal(flat_of(opt.loc_model), flat_of(model))
+
+
+@pytest.mark.parametrize("glob,loc,so,dog", [("lssr1_tr", "lssr1_tr", True, True), ("tr", "tr", True, False),
+                                             ("lssr1_tr", "tr", False, False)])
+def test_apts_d_single_rank_matches_oracle(glob, loc, so, dog):
+    g = load_golden("apts_d_tr_fo_ws1")
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    model = gpu_model(g)
+    c = cfg(glob_second_order=so, glob_dogleg=dog, loc_second_order=so, loc_dogleg=dog)
+    opt = _apts("d", model, glob, loc, c, foc=True)
+    mk_g = oracle.tr_hparams if glob == "tr" else oracle.lssr1_hparams
+    mk_l = oracle.loc_tr_hparams if loc == "tr" else oracle.lssr1_loc_hparams
+    oopt = oracle.APTSDOracle(torch.from_numpy(g["w0"]), 1, glob, mk_g(0.1, 0.01, 1.0, second_order=so, dogleg=dog),
+                              loc, mk_l(0.1, 0.01, 1.0, 1, second_order=so, dogleg=dog),
+                              **oracle.apts_hparams(0.1, 0.01, 1.0), glob_pass=True, foc=True, norm_type=2,
+                              max_loc_iters=3, max_glob_iters=1, tol=1e-6, eig_sign="canonical")
+    ofg = [make_fg(FFNN(IN_F, HID, OUT), X, Y)]
+    losses, olosses = [], []
+    Xd, Yd = X.to(DEV), Y.to(DEV)
+    first_div = None
+    for i in range(10):
+        losses.append(float(opt.step(Xd, Yd)))
+        olosses.append(float(oopt.step(ofg)))
+        if first_div is None and (abs(opt.delta - oopt.delta) > 1e-9 or rel_err(flat_of(model), oopt.w) > 1e-3):
+            first_div = i
+    print(f"apts_d {glob}/{loc} so={so}: first divergence at outer step {first_div}; {losses[-1]:.6f} vs {olosses[-1]:.6f}")
+    np.testing.assert_allclose(losses[:3], olosses[:3], rtol=5e-4)
+    assert losses[-1] < losses[0]
+    if not so:
+        np.testing.assert_allclose(losses, olosses, rtol=1e-3)
+
+
+def test_apts_p_single_rank_matches_oracle():
+    g = load_golden("apts_p_tr_fo_ws2")
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    model = gpu_model(g)
+    c = cfg(delta=0.1, min_delta=0.01, max_delta=0.5, norm_type=math.inf)
+    opt = _apts("p", model, "tr", "tr", c)
+    n = sum(p.numel() for p in model.parameters())
+    oopt = oracle.APTSPOracle(torch.from_numpy(g["w0"]), [torch.arange(n)], "tr",
+                              oracle.tr_hparams(0.1, 0.01, 0.5, norm_type=math.inf), "tr",
+                              oracle.loc_tr_hparams(0.1, 0.01, 0.5, 1, norm_type=math.inf),
+                              **oracle.apts_hparams(0.1, 0.01, 0.5), glob_pass=True, max_loc_iters=3,
+                              max_glob_iters=1, tol=1e-6)
+    ofg = [make_fg(FFNN(IN_F, HID, OUT), X, Y)]
+    losses, olosses, deltas, odeltas = [], [], [], []
+    Xd, Yd = X.to(DEV), Y.to(DEV)
+    for _ in range(10):
+        losses.append(float(opt.step(Xd, Yd))); deltas.append(opt.delta)
+        olosses.append(float(oopt.step(ofg))); odeltas.append(oopt.delta)
+    np.testing.assert_allclose(losses, olosses, rtol=1e-3)
+    np.testing.assert_allclose(deltas, odeltas, rtol=1e-9)
+    assert rel_err(flat_of(model), oopt.w) < 5e-3
+
+
+def test_optimizers_refuse_cpu_parameters():
+    model = nn.Linear(3, 2)
+    with pytest.raises(dd4ml_b200.DD4MLError):
+        TR(model.parameters(), **get_tr_hparams(cfg()))
