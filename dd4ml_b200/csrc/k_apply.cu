@@ -1,0 +1,102 @@
+// tr_apply: p = cg g + sum_j (cS_j S_j + cY_j Y_j); optional w += p; max|p|.
+#include "heavy.cuh"
+
+namespace {
+
+template <class HT, class VT, class WT, int KMAX>
+struct ApplyOp {
+    static constexpr int NRED = 1;
+    static constexpr bool SMEM_STATE = false;
+    __host__ __device__ static constexpr bool is_max(int) { return true; }
+    dd4ml_state* st;
+    const VT* g;
+    const HT* S;
+    const HT* Y;
+    VT* p;
+    WT* w;
+    int64_t ld;
+    Slots<KMAX> sl;
+    double cg, cS[KMAX > 0 ? KMAX : 1], cY[KMAX > 0 ? KMAX : 1];
+    bool conv;
+    __device__ dd4ml_state* state() const { return st; }
+    __device__ void setup() {
+        sl.load(st, true);
+        cg = st->cg[0];
+        conv = st->converged[0] != 0.0;
+        int kk = 0;  // keep only slots with non-zero coefficients (first-order step: none)
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < sl.k) {
+                const double a = st->cS[sl.slot[j]], b = st->cY[sl.slot[j]];
+                if (a != 0.0 || b != 0.0) { cS[kk] = a; cY[kk] = b; sl.slot[kk] = sl.slot[j]; ++kk; }
+            }
+        sl.k = kk;
+    }
+    __device__ bool active() const { return true; }
+    template <int V>
+    __device__ __forceinline__ void body(int64_t i, double* acc) {
+        double pv[V];
+        if (conv) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) pv[e] = 0.0;
+            st_v<V, VT>(p, i, pv);
+            return;
+        }
+        Raw<V, VT> gr;
+        Raw<V, WT> wr;
+        PairRegs<V, HT, KMAX> pr;
+        ldr_ro<V, VT>(gr, g, i);
+        if (w != nullptr) ldr_rw<V, WT>(wr, w, i);
+        pr.load(S, Y, ld, sl, i);
+#pragma unroll
+        for (int e = 0; e < V; ++e) pv[e] = cg * (double)gr.x[e];
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < sl.k) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) pv[e] += cS[j] * (double)pr.s[j].x[e] + cY[j] * (double)pr.y[j].x[e];
+            }
+#pragma unroll
+        for (int e = 0; e < V; ++e) { pv[e] = rnd<VT>(pv[e]); acc[0] = fmax(acc[0], fabs(pv[e])); }
+        st_v<V, VT>(p, i, pv);
+        if (w != nullptr) {
+            double wv[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) wv[e] = (double)wr.x[e] + pv[e];
+            st_v<V, WT>(w, i, wv);
+        }
+    }
+    __device__ void finalize(const double* s, ks::Scratch*, dd4ml_state* t) { t->pmax[0] = s[0]; }
+};
+
+}  // namespace
+
+extern "C" int dd4ml_tr_apply(double* state, double* ws, const void* g, const void* S, const void* Y, void* p,
+                              void* w, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream) {
+    if (!state || !ws || !g || !p || n < 0 || kcap > DD4ML_MAXM) return DD4ML_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = aligned16(g) && aligned16(p) && (!w || aligned16(w)) &&
+                     (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
+#define CALLK(K)                                                                                          \
+    { ApplyOp<HT_, VT_, WT_, K> op{(dd4ml_state*)state, (const VT_*)g, (const HT_*)S, (const HT_*)Y, (VT_*)p, \
+                                   (WT_*)w, ld};                                                          \
+      return launch(op, n, vec, ws, 3, s); }
+#define CALL(HT, VT, WT)                                                                                  \
+    { using HT_ = HT; using VT_ = VT; using WT_ = WT;                                                     \
+      if (!S) { ApplyOp<HT, VT, WT, 0> op{(dd4ml_state*)state, (const VT*)g, nullptr, nullptr, (VT*)p, (WT*)w, ld}; \
+                return launch(op, n, vec, ws, 4, s); }                                                    \
+      DD4ML_KCAP_SWITCH(kcap, CALLK) }
+    DT_SWITCH3(ht, vt, wt, CALL)
+#undef CALL
+#undef CALLK
+}
+
+extern "C" int dd4ml_tr_propose(double*, double*, const void*, const void*, const void*, int64_t, int64_t, int,
+                                int, int, int, void*);
+extern "C" int dd4ml_lsr1_B(double* state, double* ws, const void* v, const void* S, const void* Y, void* out,
+                            int64_t n, int64_t ld, int vt, int ht, int kcap, void* stream) {
+    if (!S || !Y) return DD4ML_E_ARG;
+    int rc = dd4ml_tr_propose(state, ws, v, S, Y, n, ld, vt, ht, 2, kcap, stream);
+    if (rc) return rc;
+    return dd4ml_tr_apply(state, ws, v, S, Y, out, nullptr, n, ld, vt, ht, vt, kcap, stream);
+}

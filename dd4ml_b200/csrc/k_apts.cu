@@ -6,12 +6,14 @@ namespace {
 template <class VT>
 struct ResidualOp {
     static constexpr int NRED = 0;
+    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     const VT* Gg;
     const VT* Gl;
     VT* g0;
     VT* gl0;
     VT* resid;
+    __device__ dd4ml_state* state() const { return nullptr; }
     __device__ void setup() {}
     __device__ bool active() const { return true; }
     template <int V>
@@ -25,12 +27,13 @@ struct ResidualOp {
         st_v<V, VT>(gl0, i, b);
         if (resid != nullptr) st_v<V, VT>(resid, i, r);
     }
-    __device__ void finalize(const double*, ks::Scratch*) {}
+    __device__ void finalize(const double*, ks::Scratch*, dd4ml_state*) {}
 };
 
 template <class VT, class WT>
 struct FocOp {
     static constexpr int NRED = 2;
+    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     dd4ml_state* st;
     const WT* wl;
@@ -40,6 +43,7 @@ struct FocOp {
     void* loss_out;
     int lt;
     double tol;
+    __device__ dd4ml_state* state() const { return st; }
     __device__ void setup() {}
     __device__ bool active() const { return true; }
     template <int V>
@@ -55,7 +59,7 @@ struct FocOp {
             acc[1] += r[e] * d;
         }
     }
-    __device__ void finalize(const double* s, ks::Scratch*) {
+    __device__ void finalize(const double* s, ks::Scratch*, dd4ml_state*) {
         st->foc_dd[0] = s[0];
         st->foc_rd[0] = s[1];
         const double l = ld_scalar(loss_in, lt);
@@ -66,6 +70,7 @@ struct FocOp {
 template <class WT>
 struct PackOp {
     static constexpr int NRED = 0;
+    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     WT* buf;
     const WT* wl;
@@ -75,6 +80,7 @@ struct PackOp {
     int lt;
     double weight, evals;
     int64_t n;
+    __device__ dd4ml_state* state() const { return nullptr; }
     __device__ void setup() {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             const double red = ld_scalar(loss0, lt) - ld_scalar(loss1, lt);
@@ -92,18 +98,20 @@ struct PackOp {
         for (int e = 0; e < V; ++e) a[e] -= b[e];
         st_v<V, WT>(buf, i, a);
     }
-    __device__ void finalize(const double*, ks::Scratch*) {}
+    __device__ void finalize(const double*, ks::Scratch*, dd4ml_state*) {}
 };
 
 template <class WT>
 struct AptsTrialOp {
     static constexpr int NRED = 0;
+    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     WT* w;
     const WT* w0;
     const WT* buf;
     int mode;
     double scale, clampv;
+    __device__ dd4ml_state* state() const { return nullptr; }
     __device__ void setup() {}
     __device__ bool active() const { return true; }
     template <int V>
@@ -120,12 +128,13 @@ struct AptsTrialOp {
         }
         st_v<V, WT>(w, i, a);
     }
-    __device__ void finalize(const double*, ks::Scratch*) {}
+    __device__ void finalize(const double*, ks::Scratch*, dd4ml_state*) {}
 };
 
 template <class VT, class WT>
 struct ControlOp {
     static constexpr int NRED = 2;
+    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
     const void* f0p;
@@ -141,6 +150,7 @@ struct ControlOp {
     const void* auxp;
     bool accept;
     double f0, f1, pred;
+    __device__ dd4ml_state* state() const { return st; }
     __device__ void setup() {
         f0 = ld_scalar(f0p, lt);
         f1 = ld_scalar(f1p, lt);
@@ -163,7 +173,7 @@ struct ControlOp {
             st_v<V, WT>(w, i, a);
         }
     }
-    __device__ void finalize(const double* s, ks::Scratch*) {
+    __device__ void finalize(const double* s, ks::Scratch*, dd4ml_state*) {
         const bool acc = (lt == 0) ? ks::apts_control<float>(st, f0, f1, pred) : ks::apts_control<double>(st, f0, f1, pred);
         if (acc) { st->out_gg[0] = s[0]; st->out_ginf[0] = s[1]; }
         st->aux[0] = auxp ? ld_scalar(auxp, pt) : 0.0;

@@ -1,0 +1,139 @@
+// lssr1_begin: first pass of LSSR1_TR.step (lssr1_tr.py:493-587).
+#include "heavy.cuh"
+
+namespace {
+
+template <class HT, class VT, class WT, int KMAX>
+struct LssrBeginOp {
+    static constexpr int NRED = 7 + 6 * KMAX;
+    static constexpr bool SMEM_STATE = true;
+    __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
+    dd4ml_state* st;
+    const WT* w;
+    WT* old_w;
+    const VT* g;
+    VT* prev_g;
+    HT* S;
+    HT* Y;
+    int64_t ld;
+    int has_prev;
+    const void* lossp;
+    int lt;
+    Slots<KMAX> sl;
+    int spare;
+    bool pair;
+    __device__ dd4ml_state* state() const { return st; }
+    __device__ void setup() {
+        sl.load(st, st->second_order[0] != 0.0);
+        spare = (int)st->spare[0];
+        pair = has_prev && st->second_order[0] != 0.0;
+    }
+    __device__ bool active() const { return true; }
+    template <int V>
+    __device__ __forceinline__ void body(int64_t i, double* acc) {
+        Raw<V, WT> wr, owr;
+        Raw<V, VT> gr, pgr;
+        PairRegs<V, HT, KMAX> pr;
+        ldr_ro<V, WT>(wr, w, i);
+        ldr_ro<V, VT>(gr, g, i);
+        if (pair) {
+            ldr_rw<V, WT>(owr, old_w, i);
+            ldr_rw<V, VT>(pgr, prev_g, i);
+        }
+        pr.load(S, Y, ld, sl, i);
+        double wv[V], gv[V], sv[V], yv[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            wv[e] = (double)wr.x[e];
+            gv[e] = (double)gr.x[e];
+            acc[0] += gv[e] * gv[e];
+            acc[1] = fmax(acc[1], fabs(gv[e]));
+        }
+        if (pair) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                sv[e] = rnd<HT>(rnd<WT>(wv[e] - (double)owr.x[e]));
+                yv[e] = rnd<HT>(rnd<VT>(gv[e] - (double)pgr.x[e]));
+                acc[2] += sv[e] * sv[e];
+                acc[3] += sv[e] * yv[e];
+                acc[4] += yv[e] * yv[e];
+                acc[5] += sv[e] * gv[e];
+                acc[6] += yv[e] * gv[e];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < sl.k) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
+                    acc[7 + j] += a * gv[e];
+                    acc[7 + KMAX + j] += b * gv[e];
+                    if (pair) {
+                        acc[7 + 2 * KMAX + j] += a * sv[e];
+                        acc[7 + 3 * KMAX + j] += b * sv[e];
+                        acc[7 + 4 * KMAX + j] += a * yv[e];
+                        acc[7 + 5 * KMAX + j] += b * yv[e];
+                    }
+                }
+            }
+        if (pair) {
+            st_v<V, HT>(S + (int64_t)spare * ld, i, sv);
+            st_v<V, HT>(Y + (int64_t)spare * ld, i, yv);
+        }
+        st_v<V, WT>(old_w, i, wv);
+        st_v<V, VT>(prev_g, i, gv);
+    }
+    __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
+        t->gg[0] = s[0];
+        t->ginf[0] = s[1];
+        t->loss[0] = ld_scalar(lossp, lt);
+        for (int j = 0; j < sl.k; ++j) { t->Sg[sl.slot[j]] = s[7 + j]; t->Yg[sl.slot[j]] = s[7 + KMAX + j]; }
+        t->pair_tried[0] = 0.0;
+        t->pair_ok[0] = 0.0;
+        t->err[0] = 0.0;
+        // lssr1_tr.py:509: the convergence test precedes the memory update
+        const double gn = (double)(VT)sqrt(s[0]);
+        if (pair && gn > t->tol[0]) {
+            t->c_ss[0] = s[2]; t->c_sy[0] = s[3]; t->c_yy[0] = s[4];
+            t->c_sg[0] = s[5]; t->c_yg[0] = s[6];
+            for (int j = 0; j < sl.k; ++j) {
+                t->c_Ss[sl.slot[j]] = s[7 + 2 * KMAX + j];
+                t->c_Ys[sl.slot[j]] = s[7 + 3 * KMAX + j];
+                t->c_Sy[sl.slot[j]] = s[7 + 4 * KMAX + j];
+                t->c_Yy[sl.slot[j]] = s[7 + 5 * KMAX + j];
+            }
+            const double tol = t->tol[0];
+            if (sqrt(s[2]) > tol && sqrt(s[4]) > tol) {  // lssr1_tr.py:521
+                t->pair_tried[0] = 1.0;
+                if (ks::lsr1_try_update(t, scr)) { t->Sg[spare] = s[5]; t->Yg[spare] = s[6]; }
+            }
+        }
+        const double ninf = t->norm_inf[0];
+        t->norm_inf[0] = 0.0;  // LSSR1_TR forces the 2-norm (lssr1_tr.py:94)
+        if (t->second_order[0] != 0.0 && t->k[0] > 0.0) ks::tr_solve<HT>(t, 1, scr);
+        else ks::tr_solve<VT>(t, 1, scr);
+        t->norm_inf[0] = ninf;
+    }
+};
+
+}  // namespace
+
+extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void* old_w, const void* g,
+                                 void* prev_g, int has_prev, void* S, void* Y, const void* loss, int lt,
+                                 int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream) {
+    if (!state || !ws || !w || !old_w || !g || !prev_g || !S || !Y || !loss || n < 0 || kcap > DD4ML_MAXM)
+        return DD4ML_E_ARG;
+    if (lt != 0 && lt != 1) return DD4ML_E_DTYPE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = aligned16(w) && aligned16(old_w) && aligned16(g) && aligned16(prev_g) && aligned16(S) &&
+                     aligned16(Y) && ld % 4 == 0;
+#define CALLK(K)                                                                                             \
+    { LssrBeginOp<HT_, VT_, WT_, K> op{(dd4ml_state*)state, (const WT_*)w, (WT_*)old_w, (const VT_*)g,       \
+          (VT_*)prev_g, (HT_*)S, (HT_*)Y, ld, has_prev, loss, lt};                                           \
+      return launch(op, n, vec, ws, K <= 4 ? 2 : 1, s); }
+#define CALL(HT, VT, WT) { using HT_ = HT; using VT_ = VT; using WT_ = WT; DD4ML_KCAP_SWITCH(kcap, CALLK) }
+    DT_SWITCH3(ht, vt, wt, CALL)
+#undef CALL
+#undef CALLK
+}

@@ -1,0 +1,222 @@
+// tr_decide (after the trial evaluation of TR.step) and the standalone LSR1.update_memory.
+#include "heavy.cuh"
+
+namespace {
+
+template <class HT, class VT, class WT, int KMAX, bool MEM>
+struct DecideOp {
+    static constexpr int NRED = 5 + 4 * KMAX;
+    static constexpr bool SMEM_STATE = true;
+    __host__ __device__ static constexpr bool is_max(int j) { return j == 4; }
+    dd4ml_state* st;
+    const void* loss;
+    const void* trial;
+    int lt;
+    const VT* gt;
+    const VT* go;
+    VT* gout;
+    const VT* p;
+    WT* w;
+    HT* S;
+    HT* Y;
+    int64_t ld;
+    Slots<KMAX> sl;
+    bool accept, conv;
+    double rho, f0, f1;
+    int spare;
+    __device__ dd4ml_state* state() const { return st; }
+    __device__ void setup() {
+        sl.load(st, MEM);
+        spare = (int)st->spare[0];
+        f0 = ld_scalar(loss, lt);
+        f1 = ld_scalar(trial, lt);
+        conv = st->converged[0] != 0.0;
+        if (conv) { accept = false; rho = 0.0; return; }
+        accept = (lt == 0) ? ks::tr_accept<float>(f0, f1, st->pred[0], st->tol[0], st->nu_dec[0], &rho)
+                           : ks::tr_accept<double>(f0, f1, st->pred[0], st->tol[0], st->nu_dec[0], &rho);
+    }
+    __device__ bool active() const { return !conv; }
+    template <int V>
+    __device__ __forceinline__ void body(int64_t i, double* acc) {
+        Raw<V, VT> prw;
+        ldr_ro<V, VT>(prw, p, i);
+        if (!accept) {  // tr.py:216 undo
+            Raw<V, WT> wr;
+            ldr_rw<V, WT>(wr, w, i);
+            double wv[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) wv[e] = (double)wr.x[e] - (double)prw.x[e];
+            st_v<V, WT>(w, i, wv);
+            return;
+        }
+        Raw<V, VT> tr, orw;
+        PairRegs<V, HT, KMAX> pr;
+        ldr_ro<V, VT>(tr, gt, i);
+        ldr_rw<V, VT>(orw, go, i);
+        if (MEM) pr.load(S, Y, ld, sl, i);
+        double tv[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            tv[e] = (double)tr.x[e];
+            acc[3] += tv[e] * tv[e];
+            acc[4] = fmax(acc[4], fabs(tv[e]));
+        }
+        if (MEM) {
+            double sv[V], yv[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                sv[e] = rnd<HT>((double)prw.x[e]);
+                yv[e] = rnd<HT>(rnd<VT>(tv[e] - (double)orw.x[e]));
+                acc[0] += sv[e] * sv[e];
+                acc[1] += sv[e] * yv[e];
+                acc[2] += yv[e] * yv[e];
+            }
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j)
+                if (j < sl.k) {
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
+                        acc[5 + j] += a * sv[e];
+                        acc[5 + KMAX + j] += b * sv[e];
+                        acc[5 + 2 * KMAX + j] += a * yv[e];
+                        acc[5 + 3 * KMAX + j] += b * yv[e];
+                    }
+                }
+            st_v<V, HT>(S + (int64_t)spare * ld, i, sv);
+            st_v<V, HT>(Y + (int64_t)spare * ld, i, yv);
+        }
+        st_v<V, VT>(gout, i, tv);
+    }
+    __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
+        t->loss[0] = f0;
+        t->trial_loss[0] = f1;
+        if (conv) {  // tr.py:147: nothing happened
+            t->accept[0] = 0.0;
+            t->out_gn[0] = t->gn[0];
+            return;
+        }
+        if (accept) {
+            t->c_ss[0] = s[0]; t->c_sy[0] = s[1]; t->c_yy[0] = s[2];
+            t->out_gg[0] = s[3]; t->out_ginf[0] = s[4];
+            for (int j = 0; j < sl.k; ++j) {
+                t->c_Ss[sl.slot[j]] = s[5 + j];
+                t->c_Ys[sl.slot[j]] = s[5 + KMAX + j];
+                t->c_Sy[sl.slot[j]] = s[5 + 2 * KMAX + j];
+                t->c_Yy[sl.slot[j]] = s[5 + 3 * KMAX + j];
+            }
+        }
+        const double so = t->second_order[0];
+        if (!MEM) t->second_order[0] = 0.0;
+        if (lt == 0) ks::tr_finish<float>(t, accept, rho, scr); else ks::tr_finish<double>(t, accept, rho, scr);
+        t->second_order[0] = so;
+        t->solve_valid[0] = 0.0;
+    }
+};
+
+// standalone LSR1.update_memory(s, y) (lsr1.py:53-144)
+template <class HT, class VT, int KMAX>
+struct UpdateOp {
+    static constexpr int NRED = 3 + 4 * KMAX;
+    static constexpr bool SMEM_STATE = true;
+    __host__ __device__ static constexpr bool is_max(int) { return false; }
+    dd4ml_state* st;
+    const VT* s_in;
+    const VT* y_in;
+    HT* S;
+    HT* Y;
+    int64_t ld;
+    Slots<KMAX> sl;
+    int spare;
+    __device__ dd4ml_state* state() const { return st; }
+    __device__ void setup() { sl.load(st, true); spare = (int)st->spare[0]; }
+    __device__ bool active() const { return true; }
+    template <int V>
+    __device__ __forceinline__ void body(int64_t i, double* acc) {
+        Raw<V, VT> sr, yr;
+        PairRegs<V, HT, KMAX> pr;
+        ldr_ro<V, VT>(sr, s_in, i);
+        ldr_ro<V, VT>(yr, y_in, i);
+        pr.load(S, Y, ld, sl, i);
+        double sv[V], yv[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            sv[e] = rnd<HT>((double)sr.x[e]);
+            yv[e] = rnd<HT>((double)yr.x[e]);
+            acc[0] += sv[e] * sv[e];
+            acc[1] += sv[e] * yv[e];
+            acc[2] += yv[e] * yv[e];
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < sl.k) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
+                    acc[3 + j] += a * sv[e];
+                    acc[3 + KMAX + j] += b * sv[e];
+                    acc[3 + 2 * KMAX + j] += a * yv[e];
+                    acc[3 + 3 * KMAX + j] += b * yv[e];
+                }
+            }
+        st_v<V, HT>(S + (int64_t)spare * ld, i, sv);
+        st_v<V, HT>(Y + (int64_t)spare * ld, i, yv);
+    }
+    __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
+        t->c_ss[0] = s[0]; t->c_sy[0] = s[1]; t->c_yy[0] = s[2];
+        for (int j = 0; j < sl.k; ++j) {
+            t->c_Ss[sl.slot[j]] = s[3 + j];
+            t->c_Ys[sl.slot[j]] = s[3 + KMAX + j];
+            t->c_Sy[sl.slot[j]] = s[3 + 2 * KMAX + j];
+            t->c_Yy[sl.slot[j]] = s[3 + 3 * KMAX + j];
+        }
+        t->err[0] = 0.0;
+        t->pair_tried[0] = 1.0;
+        ks::lsr1_try_update(t, scr);
+        t->solve_valid[0] = 0.0;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* trial_loss, int lt,
+                    const void* g_trial, const void* g_old, void* g_out, const void* p, void* w,
+                    void* S, void* Y, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream) {
+    if (!state || !ws || !loss || !trial_loss || !g_trial || !g_old || !g_out || !p || !w || n < 0 || kcap > DD4ML_MAXM)
+        return DD4ML_E_ARG;
+    if (lt != 0 && lt != 1) return DD4ML_E_DTYPE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = aligned16(g_trial) && aligned16(g_old) && aligned16(g_out) && aligned16(p) && aligned16(w) &&
+                     (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
+#define CALLK(K)                                                                                             \
+    { DecideOp<HT_, VT_, WT_, K, true> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT_*)g_trial,    \
+          (const VT_*)g_old, (VT_*)g_out, (const VT_*)p, (WT_*)w, (HT_*)S, (HT_*)Y, ld};                     \
+      return launch(op, n, vec, ws, 2, s); }
+#define CALL(HT, VT, WT)                                                                                     \
+    { using HT_ = HT; using VT_ = VT; using WT_ = WT;                                                        \
+      if (!S) { DecideOp<HT, VT, WT, 0, false> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT*)g_trial, \
+                    (const VT*)g_old, (VT*)g_out, (const VT*)p, (WT*)w, nullptr, nullptr, ld};               \
+                return launch(op, n, vec, ws, 4, s); }                                                       \
+      DD4ML_KCAP_SWITCH(kcap, CALLK) }
+    DT_SWITCH3(ht, vt, wt, CALL)
+#undef CALL
+#undef CALLK
+}
+
+int dd4ml_lsr1_update(double* state, double* ws, const void* s_in, const void* y_in, void* S, void* Y,
+                      int64_t n, int64_t ld, int vt, int ht, int kcap, void* stream) {
+    if (!state || !ws || !s_in || !y_in || !S || !Y || n < 0 || kcap > DD4ML_MAXM) return DD4ML_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = aligned16(s_in) && aligned16(y_in) && aligned16(S) && aligned16(Y) && ld % 4 == 0;
+#define CALLK(K)                                                                                             \
+    { UpdateOp<HT_, VT_, K> op{(dd4ml_state*)state, (const VT_*)s_in, (const VT_*)y_in, (HT_*)S, (HT_*)Y, ld}; \
+      return launch(op, n, vec, ws, 2, s); }
+#define CALL(HT, VT) { using HT_ = HT; using VT_ = VT; DD4ML_KCAP_SWITCH(kcap, CALLK) }
+    DT_SWITCH2(ht, vt, CALL)
+#undef CALL
+#undef CALLK
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// tr_propose: ||g||, S^T g, Y^T g in one pass + k-space sub-problem solve in the last CTA.
+#include "heavy.cuh"
+
+namespace {
+
+template <class HT, class VT, int KMAX>
+struct ProposeOp {
+    static constexpr int NRED = 2 + 2 * KMAX;
+    static constexpr bool SMEM_STATE = true;
+    __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
+    dd4ml_state* st;
+    const VT* g;
+    const HT* S;
+    const HT* Y;
+    int64_t ld;
+    int mode;
+    Slots<KMAX> sl;
+    __device__ dd4ml_state* state() const { return st; }
+    __device__ void setup() { sl.load(st, mode == 2 || st->second_order[0] != 0.0); }
+    __device__ bool active() const { return true; }
+    template <int V>
+    __device__ __forceinline__ void body(int64_t i, double* acc) {
+        Raw<V, VT> gr;
+        PairRegs<V, HT, KMAX> pr;
+        ldr_ro<V, VT>(gr, g, i);
+        pr.load(S, Y, ld, sl, i);
+        double gv[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            gv[e] = (double)gr.x[e];
+            acc[0] += gv[e] * gv[e];
+            acc[1] = fmax(acc[1], fabs(gv[e]));
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < sl.k) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    acc[2 + j] += (double)pr.s[j].x[e] * gv[e];
+                    acc[2 + KMAX + j] += (double)pr.y[j].x[e] * gv[e];
+                }
+            }
+    }
+    __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
+        t->gg[0] = s[0];
+        t->ginf[0] = s[1];
+        for (int j = 0; j < sl.k; ++j) { t->Sg[sl.slot[j]] = s[2 + j]; t->Yg[sl.slot[j]] = s[2 + KMAX + j]; }
+        if (mode == 2) ks::lsr1_B_coefs(t, scr);
+        else if (sl.k > 0) ks::tr_solve<HT>(t, mode, scr);   // OBS works in the dtype of Psi (obs.py:88)
+        else ks::tr_solve<VT>(t, mode, scr);
+    }
+};
+
+}  // namespace
+
+extern "C" int dd4ml_tr_propose(double* state, double* ws, const void* g, const void* S, const void* Y,
+                                int64_t n, int64_t ld, int vt, int ht, int mode, int kcap, void* stream) {
+    if (!state || !ws || !g || n < 0 || kcap > DD4ML_MAXM) return DD4ML_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = aligned16(g) && (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
+#define CALLK(K)                                                                                        \
+    { ProposeOp<HT_, VT_, K> op{(dd4ml_state*)state, (const VT_*)g, (const HT_*)S, (const HT_*)Y, ld, mode}; \
+      return launch(op, n, vec, ws, 3, s); }
+#define CALL(HT, VT)                                                                                    \
+    { using HT_ = HT; using VT_ = VT;                                                                   \
+      if (!S) { ProposeOp<HT, VT, 0> op{(dd4ml_state*)state, (const VT*)g, nullptr, nullptr, ld, mode}; \
+                return launch(op, n, vec, ws, 4, s); }                                                  \
+      DD4ML_KCAP_SWITCH(kcap, CALLK) }
+    DT_SWITCH2(ht, vt, CALL)
+#undef CALL
+#undef CALLK
+}

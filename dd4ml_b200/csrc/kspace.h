@@ -34,6 +34,8 @@ constexpr int MS = DD4ML_MAXS;
 constexpr double OBS_TOL = 1e-6;  // obs.py:29
 
 KS_FN inline bool finite(double x) { return x == x && fabs(x) <= 1.79769313486231570e308; }
+KS_FN inline float ks_sqrt(float x) { return sqrtf(x); }
+KS_FN inline double ks_sqrt(double x) { return sqrt(x); }
 
 // ---- dense helpers on row-major k x k blocks with leading dimension M ----------
 // R upper triangular with R^T R = G (torch.linalg.cholesky(upper=True)).
@@ -171,7 +173,7 @@ KS_FN inline void phibar_fg(T sigma, const T* Lam, const T* a, int m, T delta, T
         n2 += p * p;
         s3 += (a[j] * a[j]) / (D * D * D);
     }
-    T nrm = (T)sqrt((double)n2);
+    T nrm = ks_sqrt(n2);
     f = T(1) / nrm - T(1) / delta;
     g = s3 / (nrm * nrm * nrm);
 }
@@ -187,7 +189,7 @@ KS_FN inline T phibar_f(T sigma, const T* Lam, const T* a, int m, T delta, T tol
         T p = a[j] / (Lam[j] + sigma);
         n2 += p * p;
     }
-    return T(1) / (T)sqrt((double)n2) - T(1) / delta;
+    return T(1) / ks_sqrt(n2) - T(1) / delta;
 }
 
 template <class T>
@@ -387,7 +389,7 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode, Scratch* ws) {
         T tauT;
         T h2 = T(0);
         for (int i = 0; i <= k; ++i) { T h = a[i] / Lam[i]; h2 += h * h; }
-        if (lam_min > T(0) && (T)sqrt((double)h2) <= delT) {  // case A, obs.py:97
+        if (lam_min > T(0) && ks_sqrt(h2) <= delT) {  // case A, obs.py:97
             tauT = gamT;
             st->case_id[0] = DD4ML_CASE_A;
         } else {

@@ -79,6 +79,35 @@ __device__ __forceinline__ void st_v<1, float>(float* p, int64_t i, const double
 template <>
 __device__ __forceinline__ void st_v<1, double>(double* p, int64_t i, const double (&v)[1]) { p[i] = v[0]; }
 
+// Raw (unconverted) V-element vectors: all loads of one loop iteration are issued into these
+// BEFORE any arithmetic, so a thread has (#streams x 16 B) in flight per iteration and pays one
+// memory round trip per iteration instead of one per stream.
+template <int V, class T> struct Raw { T x[V]; };
+template <int V, class T> __device__ __forceinline__ void ldr_ro(Raw<V, T>& r, const T* __restrict__ p, int64_t i);
+template <> __device__ __forceinline__ void ldr_ro<4, float>(Raw<4, float>& r, const float* __restrict__ p, int64_t i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+    r.x[0] = t.x; r.x[1] = t.y; r.x[2] = t.z; r.x[3] = t.w;
+}
+template <> __device__ __forceinline__ void ldr_ro<4, double>(Raw<4, double>& r, const double* __restrict__ p, int64_t i) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p + i));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p + i + 2));
+    r.x[0] = a.x; r.x[1] = a.y; r.x[2] = b.x; r.x[3] = b.y;
+}
+template <> __device__ __forceinline__ void ldr_ro<1, float>(Raw<1, float>& r, const float* __restrict__ p, int64_t i) { r.x[0] = __ldg(p + i); }
+template <> __device__ __forceinline__ void ldr_ro<1, double>(Raw<1, double>& r, const double* __restrict__ p, int64_t i) { r.x[0] = __ldg(p + i); }
+template <int V, class T> __device__ __forceinline__ void ldr_rw(Raw<V, T>& r, const T* p, int64_t i);
+template <> __device__ __forceinline__ void ldr_rw<4, float>(Raw<4, float>& r, const float* p, int64_t i) {
+    const float4 t = *reinterpret_cast<const float4*>(p + i);
+    r.x[0] = t.x; r.x[1] = t.y; r.x[2] = t.z; r.x[3] = t.w;
+}
+template <> __device__ __forceinline__ void ldr_rw<4, double>(Raw<4, double>& r, const double* p, int64_t i) {
+    const double2 a = *reinterpret_cast<const double2*>(p + i);
+    const double2 b = *reinterpret_cast<const double2*>(p + i + 2);
+    r.x[0] = a.x; r.x[1] = a.y; r.x[2] = b.x; r.x[3] = b.y;
+}
+template <> __device__ __forceinline__ void ldr_rw<1, float>(Raw<1, float>& r, const float* p, int64_t i) { r.x[0] = p[i]; }
+template <> __device__ __forceinline__ void ldr_rw<1, double>(Raw<1, double>& r, const double* p, int64_t i) { r.x[0] = p[i]; }
+
 // round a double to the storage dtype and back (what a store + reload would give)
 template <class T> __device__ __forceinline__ double rnd(double x) { return (double)(T)x; }
 
@@ -167,9 +196,26 @@ __global__ void __launch_bounds__(BLOCK) stream_kernel(Op op, int64_t n, int vec
                 s_sum[j] = v;
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                *ticket = 0u;
-                op.finalize(s_sum, &s_scratch);
+            if constexpr (Op::SMEM_STATE) {
+                // The k-space routine touches the state block hundreds of times: stage it in
+                // shared memory (3 KB) instead of paying an L2 round trip per access.
+                __shared__ dd4ml_state s_state;
+                constexpr int NST = (int)(sizeof(dd4ml_state) / sizeof(double));
+                double* gst = reinterpret_cast<double*>(op.state());
+                double* sst = reinterpret_cast<double*>(&s_state);
+                for (int i = threadIdx.x; i < NST; i += BLOCK) sst[i] = __ldcg(gst + i);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    *ticket = 0u;
+                    op.finalize(s_sum, &s_scratch, &s_state);
+                }
+                __syncthreads();
+                for (int i = threadIdx.x; i < NST; i += BLOCK) gst[i] = sst[i];
+            } else {
+                if (threadIdx.x == 0) {
+                    *ticket = 0u;
+                    op.finalize(s_sum, &s_scratch, op.state());
+                }
             }
         }
     }

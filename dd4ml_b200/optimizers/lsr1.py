@@ -129,7 +129,7 @@ class LSR1:
         lib = self.ds.lib
         lib.lsr1_update(self.ds.sp, self.ds.wp, _lib.ptr(s.contiguous()), _lib.ptr(y.contiguous()),
                         self.S_ptr, self.Y_ptr, self.n, self.ld, _lib.dt(s.dtype), _lib.dt(self.dtype),
-                        _lib.stream())
+                        self.memory_length, _lib.stream())
         rep = self.ds.read()
         DeviceState.raise_for(rep.err)
         self.absorb(rep)
@@ -142,14 +142,14 @@ class LSR1:
     def B(self, v: torch.Tensor) -> torch.Tensor:
         """lsr1.py:181-198: gamma v + Psi (Minv \\ Psi^T v); two fused launches."""
         v = v.detach().flatten().contiguous()
-        if v.dtype not in (torch.float32, torch.float64):
+        if v.dtype not in (torch.float32, torch.float64) or (self.dtype == torch.float64 and v.dtype != torch.float64):
             v = v.to(self.dtype)
         out = torch.empty_like(v)
         if self._Sbuf is None:
             self.ensure_storage(v.numel())
         lib = self.ds.lib
         lib.lsr1_B(self.ds.sp, self.ds.wp, _lib.ptr(v), self.S_ptr, self.Y_ptr, _lib.ptr(out), v.numel(),
-                   self.ld, _lib.dt(v.dtype), _lib.dt(self.dtype), _lib.stream())
+                   self.ld, _lib.dt(v.dtype), _lib.dt(self.dtype), self.memory_length, _lib.stream())
         return out.to(self.dtype)
 
     # Debug / compatibility views (host-synchronising; not used on the hot path) ------

@@ -243,9 +243,9 @@ class LSSR1_TR(Optimizer):
         # the reference is an identity and is elided here.
         lib.lssr1_begin(ds.sp, ds.wp, _lib.ptr(self._fs.data), _lib.ptr(b["old_w"]), _lib.ptr(g),
                         _lib.ptr(b["prev_g"]), 1 if self._has_prev else 0, h.S_ptr, h.Y_ptr,
-                        _lib.ptr(loss_t), _lib.dt(loss_t.dtype), n, h.ld, vtc, htc, wtc, st)
+                        _lib.ptr(loss_t), _lib.dt(loss_t.dtype), n, h.ld, vtc, htc, wtc, self.mem_length, st)
         lib.tr_apply(ds.sp, ds.wp, _lib.ptr(g), h.S_ptr, h.Y_ptr, _lib.ptr(b["p"]), None, n, h.ld, vtc, htc,
-                     wtc, st)
+                     wtc, self.mem_length, st)
         rep = ds.read()
         DeviceState.raise_for(rep.err)
         h.absorb(rep)

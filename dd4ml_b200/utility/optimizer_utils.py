@@ -93,8 +93,8 @@ def solve_tr_first_order(gradient, grad_norm, trust_radius, tol):
     ds.set(delta=float(trust_radius), tol=float(tol), second_order=0.0)
     p = torch.empty_like(g)
     n, vt = g.numel(), _lib.dt(g.dtype)
-    ds.lib.tr_propose(ds.sp, ds.wp, _lib.ptr(g), None, None, n, n, vt, _lib.F32, 0, _lib.stream())
-    ds.lib.tr_apply(ds.sp, ds.wp, _lib.ptr(g), None, None, _lib.ptr(p), None, n, n, vt, _lib.F32, vt, _lib.stream())
+    ds.lib.tr_propose(ds.sp, ds.wp, _lib.ptr(g), None, None, n, n, vt, _lib.F32, 0, 0, _lib.stream())
+    ds.lib.tr_apply(ds.sp, ds.wp, _lib.ptr(g), None, None, _lib.ptr(p), None, n, n, vt, _lib.F32, vt, 0, _lib.stream())
     rep = ds.read()
     if rep.converged:
         return torch.zeros_like(g), 0.0
@@ -116,9 +116,9 @@ def solve_tr_second_order(gradient, grad_norm, trust_radius, lsr1_hessian, obs_s
     ds.set(delta=float(trust_radius), tol=float(tol), dogleg=1.0 if dogleg else 0.0, second_order=1.0,
            norm_inf=1.0 if norm_inf else 0.0)
     p = torch.empty_like(g)
-    ds.lib.tr_propose(ds.sp, ds.wp, _lib.ptr(g), h.S_ptr, h.Y_ptr, n, h.ld, vt, _lib.dt(h.dtype), 0, _lib.stream())
+    ds.lib.tr_propose(ds.sp, ds.wp, _lib.ptr(g), h.S_ptr, h.Y_ptr, n, h.ld, vt, _lib.dt(h.dtype), 0, h.memory_length, _lib.stream())
     ds.lib.tr_apply(ds.sp, ds.wp, _lib.ptr(g), h.S_ptr, h.Y_ptr, _lib.ptr(p), None, n, h.ld, vt,
-                    _lib.dt(h.dtype), vt, _lib.stream())
+                    _lib.dt(h.dtype), vt, h.memory_length, _lib.stream())
     rep = ds.read()
     DeviceState.raise_for(rep.err)
     h.absorb(rep)

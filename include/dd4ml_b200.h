@@ -15,6 +15,8 @@
  *     optimizer instance.  `ws`: device workspace of dd4ml_workspace_doubles() doubles.
  *   - S, Y     : L-SR1 pair-major ring buffers, DD4ML_MAXS slots of `ld` elements
  *     (ld >= n, ld % 4 == 0), slot j at S + j*ld.
+ *   - kcap    : the optimizer's memory length (<= DD4ML_MAXM); selects the kernel variant
+ *     unrolled for 4 or 8 live pairs.  The number of pairs actually stored is device state.
  *   - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises.
  *   - return value: 0 on success, otherwise a cudaError_t or a DD4ML_E_* code
  *     (dd4ml_error_string).  Numerical failures (Cholesky, singular solve, NaN) are
@@ -57,12 +59,12 @@ int dd4ml_state_set(double* state, int count, const int* offsets, const double* 
  *   reductions, g_out <- g_trial, L-SR1 update chain + radius update in the last CTA
  *   (lsr1.py:53-144, tr.py:193-214); rejected: w -= p, radius shrink (tr.py:216-222). */
 int dd4ml_tr_propose(double* state, double* ws, const void* g, const void* S, const void* Y,
-                     int64_t n, int64_t ld, int vt, int ht, int mode, void* stream);
+                     int64_t n, int64_t ld, int vt, int ht, int mode, int kcap, void* stream);
 int dd4ml_tr_apply(double* state, double* ws, const void* g, const void* S, const void* Y, void* p,
-                   void* w, int64_t n, int64_t ld, int vt, int ht, int wt, void* stream);
+                   void* w, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream);
 int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* trial_loss, int lt,
                     const void* g_trial, const void* g_old, void* g_out, const void* p, void* w,
-                    void* S, void* Y, int64_t n, int64_t ld, int vt, int ht, int wt, void* stream);
+                    void* S, void* Y, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream);
 
 /* ---- LSSR1_TR.step, optimizers/lssr1_tr.py:493-654 --------------------------------------
  * begin: s = w - old_w, y = g - prev_g (lssr1_tr.py:518-526) with every reduction of the
@@ -73,7 +75,7 @@ int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* tri
  * eval:  deriv = g . p, g_save <- g, loss copied into the report (lssr1_tr.py:265-271). */
 int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void* old_w, const void* g,
                       void* prev_g, int has_prev, void* S, void* Y, const void* loss, int lt,
-                      int64_t n, int64_t ld, int vt, int ht, int wt, void* stream);
+                      int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream);
 int dd4ml_lssr1_trial(void* w, const void* base, const void* p, double alpha, int64_t n, int vt,
                       int wt, void* stream);
 int dd4ml_lssr1_eval(double* state, double* ws, const void* g, const void* p, void* g_save,
@@ -118,12 +120,12 @@ int dd4ml_seg_copy(void* dst, const void* src, int count, const int64_t* dst_off
 /* ---- LSR1.update_memory, optimizers/lsr1.py:53-144: candidate reductions in one pass (the
  * pair is written to the spare ring slot), acceptance chain + Gram/gamma update in the last CTA */
 int dd4ml_lsr1_update(double* state, double* ws, const void* s, const void* y, void* S, void* Y,
-                      int64_t n, int64_t ld, int vt, int ht, void* stream);
+                      int64_t n, int64_t ld, int vt, int ht, int kcap, void* stream);
 
 /* ---- LSR1.B, optimizers/lsr1.py:181-198: out = gamma v + Psi (Minv \ Psi^T v) -------------
  * two launches: reduce (S^T v, Y^T v) + k-space solve in the last CTA, then the output pass. */
 int dd4ml_lsr1_B(double* state, double* ws, const void* v, const void* S, const void* Y, void* out,
-                 int64_t n, int64_t ld, int vt, int ht, void* stream);
+                 int64_t n, int64_t ld, int vt, int ht, int kcap, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,11 +31,18 @@ def test_first_order_solve(n, dtype, norm):
     torch.manual_seed(n)
     g = torch.randn(n, dtype=dtype)
     gn = torch.norm(g, p=norm)
-    p_ref, pred_ref = solve_first_order(g, gn, 0.37, 1e-6)
     p, pred = solve_tr_first_order(g.to(DEV), gn, 0.37, 1e-6)
-    # 1e-5 relative is the north-star tolerance for per-step vectors (fp32)
-    assert rel_err(p.cpu(), p_ref) < 1e-6
-    assert float(pred) == pytest.approx(float(pred_ref), rel=1e-6)
+    # exact arithmetic (fp64 oracle on the same fp32 data): the kernel reduces in fp64
+    g64 = g.double()
+    p64, pred64 = solve_first_order(g64, torch.norm(g64, p=norm), 0.37, 1e-6)
+    assert rel_err(p.cpu(), p64) < 2e-7 if dtype == torch.float32 else rel_err(p.cpu(), p64) < 1e-14
+    assert float(pred) == pytest.approx(float(pred64), rel=2e-7)
+    # the reference's own dtype: torch's fp32 CPU norm carries ~1e-6 (n = 2e5) ... 1e-4 (n = 4e6)
+    # accumulation error, so the 1e-5 north-star tolerance is asserted at the BASELINE sizes only
+    p_ref, pred_ref = solve_first_order(g, gn, 0.37, 1e-6)
+    if n <= 217354:
+        assert rel_err(p.cpu(), p_ref) < 1e-5
+        assert float(pred) == pytest.approx(float(pred_ref), rel=1e-5)
 
 
 def test_first_order_unaligned_pointer():
@@ -140,6 +147,7 @@ def test_cholesky_failure_raises_like_torch():
     SS = np.array(rep.SS).reshape(ms, ms); SY = np.array(rep.SY).reshape(ms, ms); YY = np.array(rep.YY).reshape(ms, ms)
     for A in (SS, SY, YY):
         A[0, 1] = A[1, 0] = A[1, 1] = A[0, 0]
+    YY[1, 1] = -abs(YY[0, 0])      # make Psi^T Psi indefinite beyond rounding
     h.ds.set_array("SS", SS.ravel()); h.ds.set_array("SY", SY.ravel()); h.ds.set_array("YY", YY.ravel())
     h.ds.set_array("order", [0, 1]); h.ds.set(k=2, spare=2)
     with pytest.raises(torch.linalg.LinAlgError):
