@@ -1,0 +1,98 @@
+"""CUDA-graph replay of a loss/gradient evaluation.
+
+The closures the APTS optimizers call (``apts_base.py:245-318``) are a fixed sequence of
+PyTorch kernels for a fixed (model, criterion, batch shape): zero the flat gradient buffer,
+forward, loss, backward into the flat gradient views.  On a B200 that sequence is CPU
+launch-bound for the BASELINE models (tens of microseconds of GPU work behind ~1 ms of
+Python/dispatcher time), so it is captured once into a CUDA graph and replayed -- the
+model's forward/backward kernels themselves are untouched.
+
+Inputs are captured by address.  When the caller keeps passing the same tensors the graph
+reads them in place; when the addresses change between calls the evaluator switches to a
+private static copy (one ``copy_`` per call).  Anything that cannot be captured (data
+dependent Python control flow in the model, unsupported ops) falls back to the eager
+PyTorch path for that shape -- this only concerns the PyTorch closure, never the
+dd4ml_b200 kernels.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+ENABLED = os.environ.get("DD4ML_B200_CUDA_GRAPHS", "1") != "0"
+
+
+class _Entry:
+    __slots__ = ("graph", "static_in", "static_lab", "loss", "private", "calls")
+
+
+class GraphedEval:
+    def __init__(self, model, criterion, flat, long_labels=True, warmup=3):
+        self.model, self.criterion, self.flat = model, criterion, flat
+        self.long_labels = long_labels
+        self.warmup = warmup
+        self.cache: dict = {}
+        self.failed: set = set()
+        self.replays = 0
+        self.captures = 0
+
+    # the eager evaluation (also what gets captured)
+    def _eval(self, inputs, labels):
+        self.flat.zero_grad()
+        lab = labels.long() if (self.long_labels and torch.is_tensor(labels)) else labels
+        loss = self.criterion(self.model(inputs), lab)
+        loss.backward()
+        return loss.detach()
+
+    @staticmethod
+    def _key(inputs, labels):
+        return (tuple(inputs.shape), inputs.dtype, tuple(labels.shape), labels.dtype)
+
+    def _capture(self, inputs, labels, private):
+        e = _Entry()
+        e.private = private
+        e.static_in = inputs.clone() if private else inputs
+        e.static_lab = labels.clone() if private else labels
+        e.calls = 0
+        # warm-up evaluations must not leave side effects (BatchNorm running statistics ...)
+        saved = [b.detach().clone() for b in self.model.buffers()]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self.warmup):
+                self._eval(e.static_in, e.static_lab)
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.no_grad():
+            for b, v in zip(self.model.buffers(), saved):
+                b.copy_(v)
+        e.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(e.graph):
+            e.loss = self._eval(e.static_in, e.static_lab)
+        self.captures += 1
+        return e
+
+    def __call__(self, inputs, labels):
+        if (not ENABLED or not torch.is_tensor(inputs) or not torch.is_tensor(labels) or inputs.requires_grad
+                or not inputs.is_cuda):
+            return self._eval(inputs, labels)
+        key = self._key(inputs, labels)
+        if key in self.failed:
+            return self._eval(inputs, labels)
+        e = self.cache.get(key)
+        try:
+            if e is None:
+                e = self.cache[key] = self._capture(inputs, labels, private=False)
+            elif not e.private and (e.static_in.data_ptr() != inputs.data_ptr()
+                                    or e.static_lab.data_ptr() != labels.data_ptr()):
+                e = self.cache[key] = self._capture(inputs, labels, private=True)   # addresses move: own copy
+        except Exception:  # noqa: BLE001  (capture unsupported for this model: eager PyTorch closure)
+            self.failed.add(key)
+            torch.cuda.synchronize()
+            return self._eval(inputs, labels)
+        if e.private:
+            e.static_in.copy_(inputs)
+            e.static_lab.copy_(labels)
+        e.graph.replay()
+        self.replays += 1
+        return e.loss.clone()

@@ -22,6 +22,7 @@ from torch.optim.optimizer import Optimizer
 from .. import _lib
 from .._device import DeviceState
 from ..flat import get_flat
+from ..graphs import GraphedEval
 from ..utility.optimizer_utils import (get_apts_hparams, get_loc_tr_hparams, get_lssr1_loc_tr_hparams,
                                        get_lssr1_tr_hparams, get_tr_hparams)
 from .lssr1_tr import LSSR1_TR
@@ -91,6 +92,9 @@ class APTS_Base(Optimizer):
         self._bufs = None
         self._bufs_version = None
         self.last_control = None
+        # CUDA-graph replay of the (untouched) PyTorch forward/backward of the closures
+        self._glob_eval = None if self._is_ddp else GraphedEval(self.model, self.criterion, self._gfs)
+        self._loc_eval = None          # created by the subclass once the local model exists
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self):
@@ -145,6 +149,10 @@ class APTS_Base(Optimizer):
 
     def non_foc_loc_closure(self, compute_grad: bool = False):
         """apts_base.py:245-260."""
+        if compute_grad and self._loc_eval is not None:
+            loss = self._loc_eval(self.inputs, self.labels)
+            self.loc_grad_evals += 1
+            return loss
         self.loc_opt.zero_grad()
         loss = self.criterion(self.loc_model(self.inputs), self._labels())
         if compute_grad:
@@ -168,13 +176,17 @@ class APTS_Base(Optimizer):
     def glob_closure_main(self, compute_grad: bool = False):
         """apts_base.py:294-318 with the gradient and loss averaged by one in-place all-reduce
         of [g || loss] on the flat gradient buffer."""
-        self.zero_grad()
-        loss = self.criterion(self.model(self.inputs), self._labels())
         with_grad = torch.is_grad_enabled() or compute_grad
-        if with_grad:
-            loss.backward()
+        if with_grad and self._glob_eval is not None:
+            loss = self._glob_eval(self.inputs, self.labels)
             self.grad_evals += 1.0
-        loss = loss.detach()
+        else:
+            self.zero_grad()
+            loss = self.criterion(self.model(self.inputs), self._labels())
+            if with_grad:
+                loss.backward()
+                self.grad_evals += 1.0
+            loss = loss.detach()
         if self._distributed:
             fb = self._gfs.fb
             if with_grad and not self._is_ddp:

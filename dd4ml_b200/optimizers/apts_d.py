@@ -58,6 +58,8 @@ class APTS_D(APTS_Base):
             self.glob_opt.delta = min(self.glob_opt.max_delta, self.delta * self.sqrt_n_global)
             self.loc_opt.delta = min(self.loc_opt.max_delta, self.delta * self.sqrt_n_local)
         self._has_buffers = any(True for _ in self.loc_model.buffers())
+        from ..graphs import GraphedEval
+        self._loc_eval = GraphedEval(self.loc_model, self.criterion, self._lfs)
 
     # ------------------------------------------------------------------ apts_base.py:228-243
     @torch.no_grad()

@@ -77,6 +77,8 @@ class APTS_P(APTS_Base):
         self._seg_all = (len(order), mk([loff[t] for t in order]), mk([goff[t] for t in order]),
                          mk([numel[t] for t in order]))
         self._has_buffers = any(True for _ in self.loc_model.buffers())
+        from ..graphs import GraphedEval
+        self._loc_eval = GraphedEval(self.loc_model, self.criterion, self._lfs)
 
     # ------------------------------------------------------------------ flat vectors (API parity)
     @torch.no_grad()
