@@ -4,19 +4,37 @@
 
 namespace {
 
-// all live S_j / Y_j vectors of one iteration, loaded before any arithmetic
+// Loader handed to Op::body_l: data straight from global memory (register staged).  The TMA
+// kernel passes a SmemLoader with the same interface (tma.cuh).
+struct GlobalLoader {
+    template <int V, class T>
+    __device__ __forceinline__ void get(int, const T* __restrict__ gptr, int64_t i, bool rw, Raw<V, T>& r) const {
+        if (rw) ldr_rw<V, T>(r, gptr, i); else ldr_ro<V, T>(r, gptr, i);
+    }
+};
+
+// all live S_j / Y_j vectors of one iteration, loaded before any arithmetic.  Stream ids:
+// S_j -> F + j, Y_j -> F + KMAX + j (F = number of fixed streams of the op).
 template <int V, class HT, int KMAX>
 struct PairRegs {
     Raw<V, HT> s[KMAX > 0 ? KMAX : 1];
     Raw<V, HT> y[KMAX > 0 ? KMAX : 1];
-    __device__ __forceinline__ void load(const HT* __restrict__ S, const HT* __restrict__ Y, int64_t ld,
-                                         const Slots<KMAX>& sl, int64_t i) {
+    template <class L>
+    __device__ __forceinline__ void load(const L& l, int F, const HT* __restrict__ S, const HT* __restrict__ Y,
+                                         int64_t ld, const Slots<KMAX>& sl, int64_t i) {
 #pragma unroll
         for (int j = 0; j < KMAX; ++j)
             if (j < sl.k) {
-                ldr_ro<V, HT>(s[j], S + (int64_t)sl.slot[j] * ld, i);
-                ldr_ro<V, HT>(y[j], Y + (int64_t)sl.slot[j] * ld, i);
+                l.template get<V, HT>(F + j, S + (int64_t)sl.slot[j] * ld, i, false, s[j]);
+                l.template get<V, HT>(F + KMAX + j, Y + (int64_t)sl.slot[j] * ld, i, false, y[j]);
             }
+    }
+    // descriptor of pair stream `r` (0 .. 2*KMAX-1) for the TMA producer
+    __device__ __forceinline__ static void desc(int r, const HT* S, const HT* Y, int64_t ld, const Slots<KMAX>& sl,
+                                                const void*& p, int& esz) {
+        const int j = r < KMAX ? r : r - KMAX;
+        esz = (int)sizeof(HT);
+        p = (j < sl.k) ? (const void*)((r < KMAX ? S : Y) + (int64_t)sl.slot[j] * ld) : nullptr;
     }
 };
 

@@ -1,5 +1,5 @@
 // tr_apply: p = cg g + sum_j (cS_j S_j + cY_j Y_j); optional w += p; max|p|.
-#include "heavy.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -7,6 +7,7 @@ template <class HT, class VT, class WT, int KMAX>
 struct ApplyOp {
     static constexpr int NRED = 1;
     static constexpr bool SMEM_STATE = false;
+    static constexpr int F = 2, NS_MAX = F + 2 * KMAX;
     __host__ __device__ static constexpr bool is_max(int) { return true; }
     dd4ml_state* st;
     const VT* g;
@@ -33,8 +34,16 @@ struct ApplyOp {
         sl.k = kk;
     }
     __device__ bool active() const { return true; }
+    __device__ bool use_tma() const { return !conv; }
+    __device__ void stream_desc(int s, const void*& p, int& esz) const {
+        if (s == 0) { p = g; esz = (int)sizeof(VT); }
+        else if (s == 1) { p = w; esz = (int)sizeof(WT); }
+        else PairRegs<4, HT, KMAX>::desc(s - F, S, Y, ld, sl, p, esz);
+    }
     template <int V>
-    __device__ __forceinline__ void body(int64_t i, double* acc) {
+    __device__ __forceinline__ void body(int64_t i, double* acc) { GlobalLoader l; body_l<V>(l, i, acc); }
+    template <int V, class L>
+    __device__ __forceinline__ void body_l(const L& l, int64_t i, double* acc) {
         double pv[V];
         if (conv) {
 #pragma unroll
@@ -45,9 +54,9 @@ struct ApplyOp {
         Raw<V, VT> gr;
         Raw<V, WT> wr;
         PairRegs<V, HT, KMAX> pr;
-        ldr_ro<V, VT>(gr, g, i);
-        if (w != nullptr) ldr_rw<V, WT>(wr, w, i);
-        pr.load(S, Y, ld, sl, i);
+        l.template get<V, VT>(0, g, i, false, gr);
+        if (w != nullptr) l.template get<V, WT>(1, w, i, true, wr);
+        pr.load(l, F, S, Y, ld, sl, i);
 #pragma unroll
         for (int e = 0; e < V; ++e) pv[e] = cg * (double)gr.x[e];
 #pragma unroll
@@ -80,7 +89,7 @@ extern "C" int dd4ml_tr_apply(double* state, double* ws, const void* g, const vo
 #define CALLK(K)                                                                                          \
     { ApplyOp<HT_, VT_, WT_, K> op{(dd4ml_state*)state, (const VT_*)g, (const HT_*)S, (const HT_*)Y, (VT_*)p, \
                                    (WT_*)w, ld};                                                          \
-      return launch(op, n, vec, ws, 3, s); }
+      return launch_heavy(op, n, vec, ws, 3, TILE * (int)(sizeof(VT_) + sizeof(WT_) + 2 * K * sizeof(HT_)), s); }
 #define CALL(HT, VT, WT)                                                                                  \
     { using HT_ = HT; using VT_ = VT; using WT_ = WT;                                                     \
       if (!S) { ApplyOp<HT, VT, WT, 0> op{(dd4ml_state*)state, (const VT*)g, nullptr, nullptr, (VT*)p, (WT*)w, ld}; \

@@ -1,5 +1,5 @@
 // lssr1_begin: first pass of LSSR1_TR.step (lssr1_tr.py:493-587).
-#include "heavy.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -7,6 +7,7 @@ template <class HT, class VT, class WT, int KMAX>
 struct LssrBeginOp {
     static constexpr int NRED = 7 + 6 * KMAX;
     static constexpr bool SMEM_STATE = true;
+    static constexpr int F = 4, NS_MAX = F + 2 * KMAX;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
     const WT* w;
@@ -29,18 +30,28 @@ struct LssrBeginOp {
         pair = has_prev && st->second_order[0] != 0.0;
     }
     __device__ bool active() const { return true; }
+    __device__ bool use_tma() const { return true; }
+    __device__ void stream_desc(int s, const void*& q, int& esz) const {
+        if (s == 0) { q = w; esz = (int)sizeof(WT); }
+        else if (s == 1) { q = g; esz = (int)sizeof(VT); }
+        else if (s == 2) { q = pair ? (const void*)old_w : nullptr; esz = (int)sizeof(WT); }
+        else if (s == 3) { q = pair ? (const void*)prev_g : nullptr; esz = (int)sizeof(VT); }
+        else PairRegs<4, HT, KMAX>::desc(s - F, S, Y, ld, sl, q, esz);
+    }
     template <int V>
-    __device__ __forceinline__ void body(int64_t i, double* acc) {
+    __device__ __forceinline__ void body(int64_t i, double* acc) { GlobalLoader l; body_l<V>(l, i, acc); }
+    template <int V, class L>
+    __device__ __forceinline__ void body_l(const L& l, int64_t i, double* acc) {
         Raw<V, WT> wr, owr;
         Raw<V, VT> gr, pgr;
         PairRegs<V, HT, KMAX> pr;
-        ldr_ro<V, WT>(wr, w, i);
-        ldr_ro<V, VT>(gr, g, i);
+        l.template get<V, WT>(0, w, i, false, wr);
+        l.template get<V, VT>(1, g, i, false, gr);
         if (pair) {
-            ldr_rw<V, WT>(owr, old_w, i);
-            ldr_rw<V, VT>(pgr, prev_g, i);
+            l.template get<V, WT>(2, old_w, i, true, owr);
+            l.template get<V, VT>(3, prev_g, i, true, pgr);
         }
-        pr.load(S, Y, ld, sl, i);
+        pr.load(l, F, S, Y, ld, sl, i);
         double wv[V], gv[V], sv[V], yv[V];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -131,7 +142,8 @@ extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void*
 #define CALLK(K)                                                                                             \
     { LssrBeginOp<HT_, VT_, WT_, K> op{(dd4ml_state*)state, (const WT_*)w, (WT_*)old_w, (const VT_*)g,       \
           (VT_*)prev_g, (HT_*)S, (HT_*)Y, ld, has_prev, loss, lt};                                           \
-      return launch(op, n, vec, ws, K <= 4 ? 2 : 1, s); }
+      return launch_heavy(op, n, vec, ws, K <= 4 ? 2 : 1,                                                     \
+                          TILE * (int)(2 * sizeof(WT_) + 2 * sizeof(VT_) + 2 * K * sizeof(HT_)), s); }
 #define CALL(HT, VT, WT) { using HT_ = HT; using VT_ = VT; using WT_ = WT; DD4ML_KCAP_SWITCH(kcap, CALLK) }
     DT_SWITCH3(ht, vt, wt, CALL)
 #undef CALL

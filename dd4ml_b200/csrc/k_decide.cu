@@ -1,5 +1,5 @@
 // tr_decide (after the trial evaluation of TR.step) and the standalone LSR1.update_memory.
-#include "heavy.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -7,6 +7,7 @@ template <class HT, class VT, class WT, int KMAX, bool MEM>
 struct DecideOp {
     static constexpr int NRED = 5 + 4 * KMAX;
     static constexpr bool SMEM_STATE = true;
+    static constexpr int F = 3, NS_MAX = F + 2 * KMAX;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 4; }
     dd4ml_state* st;
     const void* loss;
@@ -36,12 +37,23 @@ struct DecideOp {
                            : ks::tr_accept<double>(f0, f1, st->pred[0], st->tol[0], st->nu_dec[0], &rho);
     }
     __device__ bool active() const { return !conv; }
+    __device__ bool use_tma() const { return accept; }
+    __device__ void stream_desc(int s, const void*& q, int& esz) const {
+        esz = (int)sizeof(VT);
+        if (s == 0) q = p;
+        else if (s == 1) q = gt;
+        else if (s == 2) q = go;
+        else if (MEM) PairRegs<4, HT, KMAX>::desc(s - F, S, Y, ld, sl, q, esz);
+        else q = nullptr;
+    }
     template <int V>
-    __device__ __forceinline__ void body(int64_t i, double* acc) {
+    __device__ __forceinline__ void body(int64_t i, double* acc) { GlobalLoader l; body_l<V>(l, i, acc); }
+    template <int V, class L>
+    __device__ __forceinline__ void body_l(const L& l, int64_t i, double* acc) {
         Raw<V, VT> prw;
-        ldr_ro<V, VT>(prw, p, i);
-        if (!accept) {  // tr.py:216 undo
+        if (!accept) {  // tr.py:216 undo (always register staged)
             Raw<V, WT> wr;
+            ldr_ro<V, VT>(prw, p, i);
             ldr_rw<V, WT>(wr, w, i);
             double wv[V];
 #pragma unroll
@@ -51,9 +63,10 @@ struct DecideOp {
         }
         Raw<V, VT> tr, orw;
         PairRegs<V, HT, KMAX> pr;
-        ldr_ro<V, VT>(tr, gt, i);
-        ldr_rw<V, VT>(orw, go, i);
-        if (MEM) pr.load(S, Y, ld, sl, i);
+        l.template get<V, VT>(0, p, i, false, prw);
+        l.template get<V, VT>(1, gt, i, false, tr);
+        l.template get<V, VT>(2, go, i, true, orw);
+        if (MEM) pr.load(l, F, S, Y, ld, sl, i);
         double tv[V];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -119,6 +132,7 @@ template <class HT, class VT, int KMAX>
 struct UpdateOp {
     static constexpr int NRED = 3 + 4 * KMAX;
     static constexpr bool SMEM_STATE = true;
+    static constexpr int F = 2, NS_MAX = F + 2 * KMAX;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     dd4ml_state* st;
     const VT* s_in;
@@ -131,13 +145,22 @@ struct UpdateOp {
     __device__ dd4ml_state* state() const { return st; }
     __device__ void setup() { sl.load(st, true); spare = (int)st->spare[0]; }
     __device__ bool active() const { return true; }
+    __device__ bool use_tma() const { return true; }
+    __device__ void stream_desc(int s, const void*& q, int& esz) const {
+        esz = (int)sizeof(VT);
+        if (s == 0) q = s_in;
+        else if (s == 1) q = y_in;
+        else PairRegs<4, HT, KMAX>::desc(s - F, S, Y, ld, sl, q, esz);
+    }
     template <int V>
-    __device__ __forceinline__ void body(int64_t i, double* acc) {
+    __device__ __forceinline__ void body(int64_t i, double* acc) { GlobalLoader l; body_l<V>(l, i, acc); }
+    template <int V, class L>
+    __device__ __forceinline__ void body_l(const L& l, int64_t i, double* acc) {
         Raw<V, VT> sr, yr;
         PairRegs<V, HT, KMAX> pr;
-        ldr_ro<V, VT>(sr, s_in, i);
-        ldr_ro<V, VT>(yr, y_in, i);
-        pr.load(S, Y, ld, sl, i);
+        l.template get<V, VT>(0, s_in, i, false, sr);
+        l.template get<V, VT>(1, y_in, i, false, yr);
+        pr.load(l, F, S, Y, ld, sl, i);
         double sv[V], yv[V];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -193,7 +216,7 @@ int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* tri
 #define CALLK(K)                                                                                             \
     { DecideOp<HT_, VT_, WT_, K, true> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT_*)g_trial,    \
           (const VT_*)g_old, (VT_*)g_out, (const VT_*)p, (WT_*)w, (HT_*)S, (HT_*)Y, ld};                     \
-      return launch(op, n, vec, ws, 2, s); }
+      return launch_heavy(op, n, vec, ws, 2, TILE * (int)(3 * sizeof(VT_) + 2 * K * sizeof(HT_)), s); }
 #define CALL(HT, VT, WT)                                                                                     \
     { using HT_ = HT; using VT_ = VT; using WT_ = WT;                                                        \
       if (!S) { DecideOp<HT, VT, WT, 0, false> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT*)g_trial, \
@@ -212,7 +235,7 @@ int dd4ml_lsr1_update(double* state, double* ws, const void* s_in, const void* y
     const bool vec = aligned16(s_in) && aligned16(y_in) && aligned16(S) && aligned16(Y) && ld % 4 == 0;
 #define CALLK(K)                                                                                             \
     { UpdateOp<HT_, VT_, K> op{(dd4ml_state*)state, (const VT_*)s_in, (const VT_*)y_in, (HT_*)S, (HT_*)Y, ld}; \
-      return launch(op, n, vec, ws, 2, s); }
+      return launch_heavy(op, n, vec, ws, 2, TILE * (int)(2 * sizeof(VT_) + 2 * K * sizeof(HT_)), s); }
 #define CALL(HT, VT) { using HT_ = HT; using VT_ = VT; DD4ML_KCAP_SWITCH(kcap, CALLK) }
     DT_SWITCH2(ht, vt, CALL)
 #undef CALL

@@ -1,5 +1,5 @@
 // tr_propose: ||g||, S^T g, Y^T g in one pass + k-space sub-problem solve in the last CTA.
-#include "heavy.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -7,6 +7,7 @@ template <class HT, class VT, int KMAX>
 struct ProposeOp {
     static constexpr int NRED = 2 + 2 * KMAX;
     static constexpr bool SMEM_STATE = true;
+    static constexpr int F = 1, NS_MAX = F + 2 * KMAX;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
     const VT* g;
@@ -18,12 +19,19 @@ struct ProposeOp {
     __device__ dd4ml_state* state() const { return st; }
     __device__ void setup() { sl.load(st, mode == 2 || st->second_order[0] != 0.0); }
     __device__ bool active() const { return true; }
+    __device__ bool use_tma() const { return true; }
+    __device__ void stream_desc(int s, const void*& p, int& esz) const {
+        if (s == 0) { p = g; esz = (int)sizeof(VT); }
+        else PairRegs<4, HT, KMAX>::desc(s - F, S, Y, ld, sl, p, esz);
+    }
     template <int V>
-    __device__ __forceinline__ void body(int64_t i, double* acc) {
+    __device__ __forceinline__ void body(int64_t i, double* acc) { GlobalLoader l; body_l<V>(l, i, acc); }
+    template <int V, class L>
+    __device__ __forceinline__ void body_l(const L& l, int64_t i, double* acc) {
         Raw<V, VT> gr;
         PairRegs<V, HT, KMAX> pr;
-        ldr_ro<V, VT>(gr, g, i);
-        pr.load(S, Y, ld, sl, i);
+        l.template get<V, VT>(0, g, i, false, gr);
+        pr.load(l, F, S, Y, ld, sl, i);
         double gv[V];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -60,7 +68,7 @@ extern "C" int dd4ml_tr_propose(double* state, double* ws, const void* g, const 
     const bool vec = aligned16(g) && (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
 #define CALLK(K)                                                                                        \
     { ProposeOp<HT_, VT_, K> op{(dd4ml_state*)state, (const VT_*)g, (const HT_*)S, (const HT_*)Y, ld, mode}; \
-      return launch(op, n, vec, ws, 3, s); }
+      return launch_heavy(op, n, vec, ws, 3, TILE * (int)(sizeof(VT_) + 2 * K * sizeof(HT_)), s); }
 #define CALL(HT, VT)                                                                                    \
     { using HT_ = HT; using VT_ = VT;                                                                   \
       if (!S) { ProposeOp<HT, VT, 0> op{(dd4ml_state*)state, (const VT*)g, nullptr, nullptr, ld, mode}; \

@@ -26,6 +26,13 @@
 #else
 #define KS_FN
 #endif
+#if defined(__CUDA_ARCH__)
+#define KS_CLOCK() ((double)clock64())
+#define KS_RSQRT(x) rsqrt(x)
+#else
+#define KS_CLOCK() 0.0
+#define KS_RSQRT(x) (1.0 / sqrt(x))
+#endif
 
 namespace ks {
 
@@ -99,23 +106,31 @@ KS_FN inline void lu_solve(const double* LU, const int* piv, int k, double* b) {
 // Cyclic Jacobi for a symmetric k x k matrix.  On exit w ascending, V[:, j] the
 // eigenvector of w[j], each with its largest-|.| component positive (lowest index
 // on ties): the documented sign convention of this implementation.
-KS_FN inline void jacobi_eigh(double* A, int k, double* w, double* V) {
+KS_FN inline int jacobi_eigh(double* A, int k, double* w, double* V) {
     for (int i = 0; i < k; ++i)
         for (int j = 0; j < k; ++j) V[i * M + j] = (i == j) ? 1.0 : 0.0;
+    int sweeps = 0;
     for (int sweep = 0; sweep < 64; ++sweep) {
         double off = 0.0, diag = 0.0;
         for (int i = 0; i < k; ++i) {
             diag += A[i * M + i] * A[i * M + i];
             for (int j = i + 1; j < k; ++j) off += A[i * M + j] * A[i * M + j];
         }
-        if (off <= 1e-32 * diag || off == 0.0) break;
+        // off-diagonal mass below 1e-26 of the diagonal mass: eigenvalues converged to ~1e-26
+        // relative (Jacobi converges quadratically), eigenvectors to ~1e-13
+        if (off <= 1e-26 * diag || off == 0.0) break;
+        ++sweeps;
         for (int p = 0; p < k - 1; ++p)
             for (int q = p + 1; q < k; ++q) {
                 double apq = A[p * M + q];
                 if (apq == 0.0) continue;
-                double theta = (A[q * M + q] - A[p * M + p]) / (2.0 * apq);
-                double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq),
+                // written with one division and one square root
+                const double d = A[q * M + q] - A[p * M + p];
+                const double a2 = 2.0 * apq;
+                const double sg = ((d >= 0.0) == (a2 >= 0.0)) ? 1.0 : -1.0;
+                const double t = sg * fabs(a2) / (fabs(d) + sqrt(d * d + a2 * a2));
+                const double c = KS_RSQRT(t * t + 1.0), s = t * c;
                 for (int r = 0; r < k; ++r) {  // columns p, q of A
                     double arp = A[r * M + p], arq = A[r * M + q];
                     A[r * M + p] = c * arp - s * arq;
@@ -151,6 +166,7 @@ KS_FN inline void jacobi_eigh(double* A, int k, double* w, double* V) {
         if (V[im * M + j] < 0.0)
             for (int r = 0; r < k; ++r) V[r * M + j] = -V[r * M + j];
     }
+    return sweeps;
 }
 
 // ---- secular equation, in the reference's working dtype T (obs.py:184-254) -----
@@ -196,6 +212,22 @@ template <class T>
 KS_FN inline T newton(T x0, const T* Lam, const T* a, int m, T delta, T tol, int& iters, int& ndeg) {
     T x = x0, f, g;
     bool deg;
+    bool adeg = false;
+    for (int j = 0; j < m; ++j) adeg = adeg || (fabs(a[j]) < tol);
+    if (adeg) {
+        // some |a_j| < tol: phibar_fg returns (-1/delta, 1/tol) for EVERY sigma (obs.py:242-245),
+        // so the reference's loop is sigma <- sigma - f/g, 200 times (or not at all when
+        // |f| <= tol).  Same fp32/fp64 rounding sequence, without re-evaluating phibar.
+        f = T(-1) / delta;
+        g = T(1000000.0);
+        iters = 0;
+        ndeg = 1;
+        const T inc = f / g;
+        if (fabs(f) > tol)
+            for (; iters < 200; ++iters) x = x - inc;
+        ndeg += iters;
+        return x;
+    }
     phibar_fg<T>(x, Lam, a, m, delta, tol, f, g, deg);
     iters = 0;
     ndeg = deg ? 1 : 0;
@@ -287,6 +319,8 @@ template <class T>
 KS_FN inline void tr_solve(dd4ml_state* st, int mode, Scratch* ws) {
     const double delta = st->delta[0], tol = st->tol[0], gg = st->gg[0];
     const int k = (st->second_order[0] != 0.0) ? (int)st->k[0] : 0;
+    const double c_s0 = KS_CLOCK();
+    st->cyc_eigh[0] = st->cyc_newton[0] = st->jacobi_sweeps[0] = 0.0;
     for (int i = 0; i < MS; ++i) { st->cS[i] = 0.0; st->cY[i] = 0.0; }
     st->cg[0] = 0.0;
     st->err[0] = DD4ML_ERR_NONE;
@@ -359,7 +393,9 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode, Scratch* ws) {
                 double s = 0.5 * (RMR[i * M + j] + RMR[j * M + i]);
                 RMR[i * M + j] = RMR[j * M + i] = s;
             }
-        jacobi_eigh(RMR, k, D, U);
+        const double c_e0 = KS_CLOCK();
+        st->jacobi_sweeps[0] = jacobi_eigh(RMR, k, D, U);
+        st->cyc_eigh[0] = KS_CLOCK() - c_e0;
         T Lam[M + 1], a[M + 1];
         const T tolT = (T)OBS_TOL, gamT = (T)gam, delT = (T)delta;
         for (int i = 0; i < k; ++i) Lam[i] = (T)D[i] + gamT;
@@ -405,7 +441,9 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode, Scratch* ws) {
                 x0 = (sh > -lam_min) ? sh : -lam_min;
             }
             int it, nd;
+            const double c_n0 = KS_CLOCK();
             T sig = newton<T>(x0, Lam, a, k + 1, delT, tolT, it, nd);
+            st->cyc_newton[0] = KS_CLOCK() - c_n0;
             if (!finite((double)sig)) sig = newton<T>(T(0), Lam, a, k + 1, delT, tolT, it, nd);
             st->sigma0[0] = (double)x0;
             st->sigma[0] = (double)sig;
@@ -508,6 +546,7 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode, Scratch* ws) {
     st->pnorm[0] = sqrt(pp > 0.0 ? pp : 0.0);
     st->gp[0] = gp;
     st->dphi0[0] = gp;
+    st->cyc_solve[0] = KS_CLOCK() - c_s0;
 }
 
 // =================================================================================

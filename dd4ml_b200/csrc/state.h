@@ -27,7 +27,8 @@
     X(pair_ok, 1) X(loss, 1) X(trial_loss, 1) X(out_gn, 1) X(out_gg, 1)               \
     X(out_ginf, 1) X(dphi0, 1) X(flip, 1) X(clip_scale, 1) X(psq, 1) X(lam_min, 1)    \
     X(gBg, 1) X(dogleg_branch, 1) X(deriv, 1) X(eval_loss, 1) X(pmax, 1)              \
-    X(foc_dd, 1) X(foc_rd, 1) X(steps, 1) X(solve_valid, 1) X(gen, 1) X(aux, 1)                 \
+    X(foc_dd, 1) X(foc_rd, 1) X(steps, 1) X(solve_valid, 1) X(gen, 1) X(aux, 1)      \
+    X(cyc_solve, 1) X(cyc_eigh, 1) X(cyc_newton, 1) X(cyc_update, 1) X(jacobi_sweeps, 1) \
     X(report_end, 1)                                                                  \
     /* ---- L-SR1 ring bookkeeping and Gram blocks ---- */                            \
     X(spare, 1) X(order, DD4ML_MAXM)                                                  \

@@ -131,27 +131,13 @@ struct Slots {
     }
 };
 
-// ------------------------------------------------------------------ the streaming kernel
+// ------------------------------------------------------------------ reduction finish
+// warp shuffle -> shared memory -> per-CTA partials -> ticket; the last CTA sums the partials in
+// a fixed order (bit-reproducible) and runs the op's k-space routine.
 template <class Op>
-__global__ void __launch_bounds__(BLOCK) stream_kernel(Op op, int64_t n, int vec, double* ws) {
+__device__ __forceinline__ void finish_reduce(Op& op, double* acc, double* ws) {
     constexpr int NR = Op::NRED;
     constexpr int NRA = NR > 0 ? NR : 1;
-    double acc[NRA];
-#pragma unroll
-    for (int j = 0; j < NRA; ++j) acc[j] = 0.0;
-    op.setup();
-    if (op.active()) {
-        const int64_t tid = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-        const int64_t nthr = (int64_t)gridDim.x * BLOCK;
-        if (vec) {
-            const int64_t nv = n >> 2;
-            for (int64_t v = tid; v < nv; v += nthr) op.template body<4>(v << 2, acc);
-            const int64_t t = (nv << 2) + tid;
-            if (t < n) op.template body<1>(t, acc);
-        } else {
-            for (int64_t i = tid; i < n; i += nthr) op.template body<1>(i, acc);
-        }
-    }
     if constexpr (NR > 0) {
         __shared__ double s_red[NWARP][NRA];
         __shared__ double s_sum[NRA];
@@ -219,6 +205,30 @@ __global__ void __launch_bounds__(BLOCK) stream_kernel(Op op, int64_t n, int vec
             }
         }
     }
+}
+
+// ------------------------------------------------------------------ the streaming kernel
+template <class Op>
+__global__ void __launch_bounds__(BLOCK) stream_kernel(Op op, int64_t n, int vec, double* ws) {
+    constexpr int NR = Op::NRED;
+    constexpr int NRA = NR > 0 ? NR : 1;
+    double acc[NRA];
+#pragma unroll
+    for (int j = 0; j < NRA; ++j) acc[j] = 0.0;
+    op.setup();
+    if (op.active()) {
+        const int64_t tid = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+        const int64_t nthr = (int64_t)gridDim.x * BLOCK;
+        if (vec) {
+            const int64_t nv = n >> 2;
+            for (int64_t v = tid; v < nv; v += nthr) op.template body<4>(v << 2, acc);
+            const int64_t t = (nv << 2) + tid;
+            if (t < n) op.template body<1>(t, acc);
+        } else {
+            for (int64_t i = tid; i < n; i += nthr) op.template body<1>(i, acc);
+        }
+    }
+    finish_reduce(op, acc, ws);
 }
 
 static_assert(BLOCK >= MAXRED, "one thread per reduction column in the finish");

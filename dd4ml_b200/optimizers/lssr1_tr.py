@@ -291,7 +291,9 @@ class LSSR1_TR(Optimizer):
                 self.delta = max(self.min_delta, self.nu_3 * self.delta)
         self.last_report = dict(gn=rep.gn, pred=float(pred), rho=rho, alpha=float(alpha), k=int(rep.k),
                                 evals=self.n_evals - n0, d0=float(d0), case=int(rep.case_id),
-                                sigma=rep.sigma, pair_ok=rep.pair_ok, pair_tried=rep.pair_tried)
+                                sigma=rep.sigma, pair_ok=rep.pair_ok, pair_tried=rep.pair_tried,
+                                cyc_solve=rep.cyc_solve, cyc_eigh=rep.cyc_eigh, cyc_newton=rep.cyc_newton,
+                                newton_iters=rep.newton_iters, jacobi_sweeps=rep.jacobi_sweeps)
         self.last_grad_norm = None
         return new_loss, new_g
 

@@ -1,0 +1,47 @@
+"""Re-run the kernel and optimizer parity tests with every vector routed through the
+TMA-staged kernels (DD4ML_B200_TMA_MIN_N=0; by default only n >= 2^20 takes that path)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_parity_suite_through_tma_kernels():
+    env = dict(os.environ, DD4ML_B200_TMA_MIN_N="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_kernels.py"),
+                        os.path.join(HERE, "test_gpu_optimizers.py"), "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+def test_large_vectors_take_the_tma_path_and_match_torch():
+    """n = 2^21 + 4 (> default threshold): lsr1 update / B / second-order solve vs fp64 torch."""
+    import dd4ml_b200
+    from dd4ml_b200.optimizers.lsr1 import LSR1
+    torch.manual_seed(11)
+    n, dev = (1 << 21) + 4, "cuda"
+    h = LSR1(gamma=1.0, memory_length=3, tol=1e-6, device=dev)
+    S, Y = [], []
+    for i in range(4):
+        s = torch.randn(n, device=dev) * 0.01
+        y = (1.0 + 0.3 * i) * s + 0.002 * torch.randn(n, device=dev)
+        h.update_memory(s, y)
+        S.append(s); Y.append(y)
+    assert len(h._S) == 3
+    S, Y = torch.stack(S[1:], 1).double(), torch.stack(Y[1:], 1).double()
+    gam = float(h.gamma)
+    assert gam == pytest.approx(float((Y[:, -1] @ Y[:, -1]) / (Y[:, -1] @ S[:, -1])), rel=1e-6)
+    Psi = Y - gam * S
+    SY = S.t() @ Y
+    Minv = torch.diag(torch.diag(SY)) + torch.tril(SY, -1) + torch.tril(SY, -1).t() - gam * (S.t() @ S)
+    Minv = Minv + 1e-6 * torch.linalg.norm(Minv) * torch.eye(3, device=dev, dtype=torch.float64)
+    v = torch.randn(n, device=dev)
+    Bv = gam * v.double() + Psi @ torch.linalg.solve(Minv, Psi.t() @ v.double())
+    got = h.B(v).double()
+    assert float((got - Bv).norm() / Bv.norm()) < 1e-6
+    assert torch.equal(h.S, S.float()) and torch.equal(h.Y, Y.float())
