@@ -68,7 +68,7 @@ extern "C" int dd4ml_tr_propose(double* state, double* ws, const void* g, const 
     const bool vec = aligned16(g) && (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
 #define CALLK(K)                                                                                        \
     { ProposeOp<HT_, VT_, K> op{(dd4ml_state*)state, (const VT_*)g, (const HT_*)S, (const HT_*)Y, ld, mode}; \
-      return launch_heavy(op, n, vec, ws, 3, TILE * (int)(sizeof(VT_) + 2 * K * sizeof(HT_)), s); }
+      return launch_heavy(op, n, vec, ws, 3, TILE * (int)(sizeof(VT_) + 2 * K * sizeof(HT_)), false, s); }
 #define CALL(HT, VT)                                                                                    \
     { using HT_ = HT; using VT_ = VT;                                                                   \
       if (!S) { ProposeOp<HT, VT, 0> op{(dd4ml_state*)state, (const VT*)g, nullptr, nullptr, ld, mode}; \

@@ -134,12 +134,12 @@ struct Slots {
 // ------------------------------------------------------------------ reduction finish
 // warp shuffle -> shared memory -> per-CTA partials -> ticket; the last CTA sums the partials in
 // a fixed order (bit-reproducible) and runs the op's k-space routine.
-template <class Op>
+template <class Op, int NW = NWARP>
 __device__ __forceinline__ void finish_reduce(Op& op, double* acc, double* ws) {
     constexpr int NR = Op::NRED;
     constexpr int NRA = NR > 0 ? NR : 1;
     if constexpr (NR > 0) {
-        __shared__ double s_red[NWARP][NRA];
+        __shared__ double s_red[NW][NRA];
         __shared__ double s_sum[NRA];
         __shared__ int s_last;
         __shared__ ks::Scratch s_scratch;
@@ -160,7 +160,7 @@ __device__ __forceinline__ void finish_reduce(Op& op, double* acc, double* ws) {
         if (threadIdx.x < NR) {
             const int j = threadIdx.x;
             double v = s_red[0][j];
-            for (int w = 1; w < NWARP; ++w) v = Op::is_max(j) ? fmax(v, s_red[w][j]) : v + s_red[w][j];
+            for (int w = 1; w < NW; ++w) v = Op::is_max(j) ? fmax(v, s_red[w][j]) : v + s_red[w][j];
             partials[(int64_t)blockIdx.x * NR + j] = v;
             __threadfence();
         }
@@ -189,14 +189,14 @@ __device__ __forceinline__ void finish_reduce(Op& op, double* acc, double* ws) {
                 constexpr int NST = (int)(sizeof(dd4ml_state) / sizeof(double));
                 double* gst = reinterpret_cast<double*>(op.state());
                 double* sst = reinterpret_cast<double*>(&s_state);
-                for (int i = threadIdx.x; i < NST; i += BLOCK) sst[i] = __ldcg(gst + i);
+                for (int i = threadIdx.x; i < NST; i += NW * 32) sst[i] = __ldcg(gst + i);
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     *ticket = 0u;
                     op.finalize(s_sum, &s_scratch, &s_state);
                 }
                 __syncthreads();
-                for (int i = threadIdx.x; i < NST; i += BLOCK) gst[i] = sst[i];
+                for (int i = threadIdx.x; i < NST; i += NW * 32) gst[i] = sst[i];
             } else {
                 if (threadIdx.x == 0) {
                     *ticket = 0u;

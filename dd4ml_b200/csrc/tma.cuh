@@ -67,10 +67,21 @@ struct SmemLoader {
     }
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 8 consumer warps + 1 producer warp.  full[s]: armed by the producer with the byte count of the
+// stage, completed by the TMA unit.  empty[s]: one arrival per consumer warp when it has read
+// the stage; the producer waits for it before refilling.  No CTA-wide barrier in the loop, so
+// the warps drift apart by up to `nstage` tiles and hide each other's latencies.
+constexpr int TMA_THREADS = BLOCK + 32;
+
 template <class Op>
-__global__ void __launch_bounds__(BLOCK, 1) tma_kernel(Op op, int64_t n, double* ws, int nstage, int stage_bytes) {
+__global__ void __launch_bounds__(TMA_THREADS, 1) tma_kernel(Op op, int64_t n, double* ws, int nstage, int stage_bytes) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) uint64_t full[MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty[MAX_STAGES];
     __shared__ const void* s_ptr[Op::NS_MAX];
     __shared__ int s_esz[Op::NS_MAX];
     __shared__ int s_off[Op::NS_MAX];
@@ -80,6 +91,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tma_kernel(Op op, int64_t n, double*
 #pragma unroll
     for (int j = 0; j < NRA; ++j) acc[j] = 0.0;
     op.setup();
+    const bool producer = threadIdx.x >= BLOCK;
     if (threadIdx.x == 0) {
         int off = 0;
         for (int s = 0; s < Op::NS_MAX; ++s) {
@@ -91,7 +103,7 @@ __global__ void __launch_bounds__(BLOCK, 1) tma_kernel(Op op, int64_t n, double*
             s_off[s] = off;
             if (p) off += TILE * esz;
         }
-        for (int s = 0; s < nstage; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -99,48 +111,48 @@ __global__ void __launch_bounds__(BLOCK, 1) tma_kernel(Op op, int64_t n, double*
         const int64_t nv4 = n & ~(int64_t)3;
         if (op.use_tma()) {
             const int64_t ntiles = (nv4 + TILE - 1) / TILE;
-            auto issue = [&](int64_t t, int stg) {
-                const int64_t e0 = t * TILE;
-                const int64_t cnt = (nv4 - e0 < TILE) ? (nv4 - e0) : TILE;
-                uint32_t total = 0;
-                for (int s = 0; s < Op::NS_MAX; ++s) total += (uint32_t)(cnt * s_esz[s]);
-                mbar_expect_tx(&full[stg], total);
-                unsigned char* base = ring + (size_t)stg * stage_bytes;
-                for (int s = 0; s < Op::NS_MAX; ++s)
-                    if (s_esz[s])
-                        bulk_g2s(base + s_off[s], reinterpret_cast<const unsigned char*>(s_ptr[s]) + e0 * s_esz[s],
-                                 (uint32_t)(cnt * s_esz[s]), &full[stg]);
-            };
-            if (threadIdx.x == 0)
-                for (int j = 0; j < nstage - 1; ++j) {
-                    const int64_t t = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
-                    if (t < ntiles) issue(t, j);
+            if (producer) {
+                if (threadIdx.x == BLOCK) {
+                    int it = 0;
+                    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                        const int stg = it % nstage;
+                        if (it >= nstage) mbar_wait(&empty[stg], (uint32_t)(((it / nstage) - 1) & 1));
+                        const int64_t e0 = t * TILE;
+                        const int64_t cnt = (nv4 - e0 < TILE) ? (nv4 - e0) : TILE;
+                        uint32_t total = 0;
+                        for (int s = 0; s < Op::NS_MAX; ++s) total += (uint32_t)(cnt * s_esz[s]);
+                        mbar_expect_tx(&full[stg], total);
+                        unsigned char* base = ring + (size_t)stg * stage_bytes;
+                        for (int s = 0; s < Op::NS_MAX; ++s)
+                            if (s_esz[s])
+                                bulk_g2s(base + s_off[s],
+                                         reinterpret_cast<const unsigned char*>(s_ptr[s]) + e0 * s_esz[s],
+                                         (uint32_t)(cnt * s_esz[s]), &full[stg]);
+                    }
                 }
-            int it = 0;
-            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const int stg = it % nstage;
-                const uint32_t ph = (uint32_t)((it / nstage) & 1);
-                if (threadIdx.x == 0) {
-                    const int64_t tn = t + (int64_t)(nstage - 1) * gridDim.x;
-                    if (tn < ntiles) issue(tn, (it + nstage - 1) % nstage);
+            } else {
+                int it = 0;
+                for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                    const int stg = it % nstage;
+                    mbar_wait(&full[stg], (uint32_t)((it / nstage) & 1));
+                    const int64_t i0 = t * TILE + (int64_t)threadIdx.x * 4;
+                    if (i0 < nv4) {
+                        SmemLoader ld{ring + (size_t)stg * stage_bytes, s_off, (int)threadIdx.x * 4};
+                        op.template body_l<4>(ld, i0, acc);
+                    }
+                    __syncwarp();
+                    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stg]);
                 }
-                mbar_wait(&full[stg], ph);
-                const int64_t i0 = t * TILE + (int64_t)threadIdx.x * 4;
-                if (i0 < nv4) {
-                    SmemLoader ld{ring + (size_t)stg * stage_bytes, s_off, (int)threadIdx.x * 4};
-                    op.template body_l<4>(ld, i0, acc);
-                }
-                __syncthreads();  // every thread is done with this stage before it is refilled
             }
-        } else {
+        } else if (!producer) {
             const int64_t tid = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
             const int64_t nthr = (int64_t)gridDim.x * BLOCK;
             for (int64_t v = tid; v < (nv4 >> 2); v += nthr) op.template body<4>(v << 2, acc);
         }
         const int64_t tt = nv4 + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-        if (tt < n) op.template body<1>(tt, acc);
+        if (!producer && tt < n) op.template body<1>(tt, acc);
     }
-    finish_reduce(op, acc, ws);
+    finish_reduce<Op, NWARP + 1>(op, acc, ws);
 }
 
 // vectors at least this long go through the TMA ring (smaller ones are L2 resident and
@@ -154,12 +166,23 @@ inline int64_t tma_min_n() {
     return v;
 }
 
+inline int tma_mode() {   // 0: per-op default, 1: every heavy op, 2: none
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DD4ML_B200_TMA_MODE");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 template <class Op>
-inline int launch_heavy(Op op, int64_t n, bool vec, double* ws, int per_sm, int stage_bytes, cudaStream_t s) {
+inline int launch_heavy(Op op, int64_t n, bool vec, double* ws, int per_sm, int stage_bytes, bool tma_default,
+                        cudaStream_t s) {
     static_assert(Op::NRED <= MAXRED, "too many fused reductions");
     int nstage = stage_bytes > 0 ? SMEM_BUDGET / stage_bytes : 0;
     if (nstage > MAX_STAGES) nstage = MAX_STAGES;
-    if (!vec || nstage < 2 || n < tma_min_n()) return launch(op, n, vec, ws, per_sm, s);
+    const bool want = tma_mode() == 1 || (tma_mode() == 0 && tma_default);
+    if (!want || !vec || nstage < 2 || n < tma_min_n()) return launch(op, n, vec, ws, per_sm, s);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tma_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
@@ -168,7 +191,7 @@ inline int launch_heavy(Op op, int64_t n, bool vec, double* ws, int per_sm, int 
     }
     const int64_t ntiles = ((n & ~(int64_t)3) + TILE - 1) / TILE;
     int grid = (int)(ntiles < NUM_SMS ? (ntiles < 1 ? 1 : ntiles) : NUM_SMS);
-    tma_kernel<Op><<<grid, BLOCK, (size_t)nstage * stage_bytes, s>>>(op, n, ws, nstage, stage_bytes);
+    tma_kernel<Op><<<grid, TMA_THREADS, (size_t)nstage * stage_bytes, s>>>(op, n, ws, nstage, stage_bytes);
     return (int)cudaGetLastError();
 }
 

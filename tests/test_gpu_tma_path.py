@@ -1,5 +1,6 @@
 """Re-run the kernel and optimizer parity tests with every vector routed through the
-TMA-staged kernels (DD4ML_B200_TMA_MIN_N=0; by default only n >= 2^20 takes that path)."""
+TMA-staged kernels (DD4ML_B200_TMA_MIN_N=0, DD4ML_B200_TMA_MODE=1; by default only the
+update/decide/begin ops at n >= 2^20 take that path)."""
 import os
 import subprocess
 import sys
@@ -12,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def test_parity_suite_through_tma_kernels():
-    env = dict(os.environ, DD4ML_B200_TMA_MIN_N="0")
+    env = dict(os.environ, DD4ML_B200_TMA_MIN_N="0", DD4ML_B200_TMA_MODE="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_kernels.py"),
                         os.path.join(HERE, "test_gpu_optimizers.py"), "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=1200)
