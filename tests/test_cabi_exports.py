@@ -68,3 +68,34 @@ def test_hparam_tables_match_reference_values():
     assert l["sync"] is False and l["delta"] == c.delta
     c.norm_type = math.inf
     assert get_loc_tr_hparams(c)["delta"] == c.delta
+
+
+def test_install_overlays_reference_module_paths(monkeypatch):
+    """dd4ml_b200.install(): DD4ML's late imports (trainer_setup.py:231-345) resolve to the B200 classes."""
+    import sys
+    import types
+    import dd4ml_b200
+    for name in ("dd4ml", "dd4ml.optimizers", "dd4ml.solvers"):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            mod.__path__ = []
+            monkeypatch.setitem(sys.modules, name, mod)
+    done = dd4ml_b200.install()
+    try:
+        from dd4ml.optimizers.apts_d import APTS_D
+        from dd4ml.optimizers.apts_p import APTS_P
+        from dd4ml.optimizers.apts_pinn import APTS_PINN
+        from dd4ml.optimizers.lssr1_tr import LSSR1_TR
+        from dd4ml.optimizers.tr import TR
+        from dd4ml.optimizers.lsr1 import LSR1
+        from dd4ml.solvers.obs import OBS
+        assert APTS_D is dd4ml_b200.APTS_D and APTS_P is dd4ml_b200.APTS_P and APTS_PINN is dd4ml_b200.APTS_PINN
+        assert TR is dd4ml_b200.TR and LSSR1_TR is dd4ml_b200.LSSR1_TR and LSR1 is dd4ml_b200.LSR1 and OBS is dd4ml_b200.OBS
+        # class names keep the substrings the reference Trainer dispatches on (trainer.py:163-168,924-927)
+        assert "apts_d" in APTS_D.__name__.lower() and "apts_pinn" in APTS_PINN.__name__.lower()
+        from dd4ml_b200.workloads import apts_d_yaml_config
+        cfg = APTS_D.setup_APTS_hparams(apts_d_yaml_config())
+        assert cfg.glob_opt is LSSR1_TR and cfg.loc_opt is LSSR1_TR and cfg.glob_opt_hparams["sync"] is True
+    finally:
+        for k in done:
+            sys.modules.pop(k, None)
