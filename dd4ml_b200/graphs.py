@@ -42,7 +42,9 @@ class GraphedEval:
         self.flat.zero_grad()
         lab = labels.long() if (self.long_labels and torch.is_tensor(labels)) else labels
         loss = self.criterion(self.model(inputs), lab)
-        loss.backward()
+        # inputs that carry autograd history (APTS_PINN: sub_in = full_in[mask]) are evaluated
+        # several times per step; like the reference (apts_base.py:258) keep their graph alive
+        loss.backward(retain_graph=bool(torch.is_tensor(inputs) and inputs.requires_grad))
         return loss.detach()
 
     @staticmethod

@@ -156,7 +156,7 @@ class APTS_Base(Optimizer):
         self.loc_opt.zero_grad()
         loss = self.criterion(self.loc_model(self.inputs), self._labels())
         if compute_grad:
-            loss.backward()
+            loss.backward(retain_graph=bool(torch.is_tensor(self.inputs) and self.inputs.requires_grad))
             self.loc_grad_evals += 1
         return loss.detach()
 

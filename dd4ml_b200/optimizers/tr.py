@@ -193,9 +193,10 @@ class TR(Optimizer):
         else:
             S = Y = None
             ld, ht = n, _lib.F32
+        kcap = self.mem_length if h is not None else 0
         vtc, wtc = _lib.dt(vt), _lib.dt(w.dtype)
 
-        lib.tr_propose(ds.sp, ds.wp, _lib.ptr(grad), S, Y, n, ld, vtc, ht, 0, self.mem_length, st)
+        lib.tr_propose(ds.sp, ds.wp, _lib.ptr(grad), S, Y, n, ld, vtc, ht, 0, kcap, st)
         # convergence test (tr.py:147): ||g|| is already known on the host when `grad` is the
         # vector this optimizer returned last time; otherwise one extra report read.
         kg = self._known_gn
@@ -211,7 +212,7 @@ class TR(Optimizer):
 
         self._step_buf = b["step"]
         lib.tr_apply(ds.sp, ds.wp, _lib.ptr(grad), S, Y, _lib.ptr(self._step_buf), _lib.ptr(w), n, ld,
-                     vtc, ht, wtc, self.mem_length, st)
+                     vtc, ht, wtc, kcap, st)
         if self._flat_params_fn is not None:
             torch.nn.utils.vector_to_parameters(w, self.ps)
         trial_loss = closure(compute_grad=True)
@@ -222,7 +223,7 @@ class TR(Optimizer):
         g_out = b["g_out"]
         lib.tr_decide(ds.sp, ds.wp, _lib.ptr(loss_t), _lib.ptr(trial_t), _lib.dt(loss_t.dtype), _lib.ptr(G),
                       _lib.ptr(grad), _lib.ptr(g_out), _lib.ptr(self._step_buf), _lib.ptr(w), S, Y, n, ld,
-                      vtc, ht, wtc, self.mem_length, st)
+                      vtc, ht, wtc, kcap, st)
         rep = ds.read()
         DeviceState.raise_for(rep.err)
         self.last_report = rep

@@ -73,3 +73,26 @@ def rel_err(a, b):
     a = torch.as_tensor(a, dtype=torch.float64)
     b = torch.as_tensor(b, dtype=torch.float64)
     return float((a - b).norm() / max(float(b.norm()), 1e-300))
+
+
+def noisy_fg(fg, eps, gen):
+    """fg with every evaluation perturbed by a relative `eps` (size of GPU-vs-CPU rounding of the model)."""
+    def f(w):
+        l, g = fg(w)
+        if eps > 0:
+            g = g * (1 + eps * torch.randn(g.shape, generator=gen, dtype=g.dtype))
+            l = l * (1 + eps * float(torch.randn((), generator=gen)))
+        return l, g
+    return f
+
+
+def branch_distance(gpu_losses, oracle_run, k, seeds=10, eps=1e-6):
+    """Second-order TR trajectories branch on discrete decisions (L-SR1 pair acceptance, Wolfe/zoom
+    exits, accept/reject) that flip under 1e-6 perturbations; the oracle itself reaches a handful of
+    distinct branches.  Returns the smallest max-relative distance over the first k losses between
+    the GPU run and the oracle branches reached with relative-eps perturbed evaluations.
+    oracle_run(eps, seed) -> list of losses."""
+    runs = [oracle_run(0.0, 0)] + [oracle_run(eps, s) for s in range(seeds)]
+    gpu = np.asarray(gpu_losses[:k], dtype=np.float64)
+    d = [float(np.max(np.abs(gpu - np.asarray(r[:k])) / np.abs(np.asarray(r[:k])))) for r in runs]
+    return min(d), runs[int(np.argmin(d))]
