@@ -89,7 +89,7 @@ extern "C" int dd4ml_tr_apply(double* state, double* ws, const void* g, const vo
 #define CALLK(K)                                                                                          \
     { ApplyOp<HT_, VT_, WT_, K> op{(dd4ml_state*)state, (const VT_*)g, (const HT_*)S, (const HT_*)Y, (VT_*)p, \
                                    (WT_*)w, ld};                                                          \
-      return launch_heavy(op, n, vec, ws, 3, TILE * (int)(sizeof(VT_) + sizeof(WT_) + 2 * K * sizeof(HT_)), K <= 4, s); }
+      return launch_heavy(op, n, vec, ws, 3, TILE * (int)(sizeof(VT_) + sizeof(WT_) + 2 * K * sizeof(HT_)), K <= 6, s); }
 #define CALL(HT, VT, WT)                                                                                  \
     { using HT_ = HT; using VT_ = VT; using WT_ = WT;                                                     \
       if (!S) { ApplyOp<HT, VT, WT, 0> op{(dd4ml_state*)state, (const VT*)g, nullptr, nullptr, (VT*)p, (WT*)w, ld}; \

@@ -309,6 +309,13 @@ KS_FN inline double step_gp(const Compact& C, const double* b, double gg, const 
     return s.cg * gg + dotk(s.c, b, C.k);
 }
 
+// register-resident variants for k <= 4 (kspace_small.h, included at the end of this file)
+template <class T, int K>
+KS_FN bool second_order_s(dd4ml_state* st, double gn, double gg, double delta, double& cg_out, double (&c_out)[M],
+                          double& pred, double& pp, double& gp);
+template <int K>
+KS_FN bool update_us_uu_s(dd4ml_state* st, double ss, double sy, double yy, double& us, double& uu);
+
 // =================================================================================
 // The trust-region sub-problem.  mode 0: TR (tr.py:150-176), mode 1: LSSR1_TR
 // (additionally clip to the radius and flip to a descent direction,
@@ -357,6 +364,17 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode, Scratch* ws) {
         pp = S.cg * S.cg * gg;
         gp = S.cg * gg;
         st->case_id[0] = DD4ML_CASE_FIRST_ORDER;
+    } else if (k <= 4) {
+        bool ok;
+        switch (k) {
+            case 1: ok = second_order_s<T, 1>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
+            case 2: ok = second_order_s<T, 2>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
+            case 3: ok = second_order_s<T, 3>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
+            default: ok = second_order_s<T, 4>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
+        }
+        if (!ok) { st->solve_valid[0] = 0.0; return; }
+        C.k = k;
+        C.gamma = st->gamma[0];
     } else {
         build_compact(st, C);
         const double gam = C.gamma;
@@ -569,6 +587,15 @@ KS_FN inline bool lsr1_try_update(dd4ml_state* st, Scratch* ws) {
     if (k == 0) {  // B = gamma I
         us = sy - gam * ss;
         uu = yy - 2.0 * gam * sy + gam * gam * ss;
+    } else if (k <= 4) {
+        bool ok;
+        switch (k) {
+            case 1: ok = update_us_uu_s<1>(st, ss, sy, yy, us, uu); break;
+            case 2: ok = update_us_uu_s<2>(st, ss, sy, yy, us, uu); break;
+            case 3: ok = update_us_uu_s<3>(st, ss, sy, yy, us, uu); break;
+            default: ok = update_us_uu_s<4>(st, ss, sy, yy, us, uu); break;
+        }
+        if (!ok) return false;
     } else {
         Compact& C = ws->C;
         build_compact(st, C);
@@ -739,3 +766,5 @@ KS_FN inline bool apts_control(dd4ml_state* st, double f0, double ftrial, double
 }
 
 }  // namespace ks
+
+#include "kspace_small.h"

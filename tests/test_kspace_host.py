@@ -256,3 +256,37 @@ def test_apts_control_rules(shim):
     assert lib.hostshim_apts_control(hs.ptr(), 1.0, 0.5, 1e-9, 1) == 0
     hs = HostState(lib, lay, m=3, **hp)   # accepted, moderate rho: keep delta
     assert lib.hostshim_apts_control(hs.ptr(), 1.0, 0.95, 0.1, 1) == 1 and hs.get("delta") == pytest.approx(0.1)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 8])
+@pytest.mark.parametrize("dog", [False, True])
+def test_second_order_all_memory_sizes_vs_fp64_oracle(shim, k, dog):
+    """k = 1..4 run the register-resident solvers (kspace_small.h), k >= 5 the generic ones; both
+    against the oracle evaluated in fp64 on the same (fp32) data."""
+    lib, lay = shim
+    torch.manual_seed(100 + k)
+    n = 400
+    diag = torch.linspace(0.2, 3.0, n)
+    hc = LSR1Memory(gamma=1.0, memory_length=k, tol=1e-6, dtype=torch.float64)
+    hs = HostState(lib, lay, m=k, second_order=1, dogleg=int(dog))
+    hs.set(k=0, gamma=1.0, spare=0)
+    for _ in range(k):
+        s = (torch.randn(n) * 0.05)
+        y = (diag * s + 0.01 * torch.randn(n))
+        assert hc.update(s.double(), y.double())
+        hc.precompute()
+        hs.candidate(s, y)
+        assert lib.hostshim_try_update(hs.ptr()) == 1
+    assert int(hs.get("k")) == k
+    assert hs.get("gamma") == pytest.approx(float(hc.gamma), rel=1e-12)
+    for delta in (0.02, 0.5, 20.0):
+        g = torch.randn(n)
+        hs.set(delta=delta)
+        p = hs.solve(g, is_float=0)
+        assert hs.get("err") == 0
+        info = {}
+        p_or, pred_or = solve_second_order(g.double(), torch.norm(g.double()), delta, hc, 1e-6, dogleg=dog,
+                                           eig_sign="canonical", info=info)
+        assert {"A": 1, "C": 3}[info["case"]] == int(hs.get("case_id"))
+        assert rel_err(p, p_or) < 1e-8
+        assert hs.get("pred") == pytest.approx(float(pred_or), rel=1e-7, abs=1e-12)
