@@ -168,6 +168,13 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
         "dd4ml_lssr1_eval": lambda: lib.lssr1_eval(ds.sp, ds.wp, gv.data_ptr(), p.data_ptr(), prev_g.data_ptr(),
                                                    loss.data_ptr(), 0, n, 0, st),
     }
+    trial_l = torch.tensor(0.5, device=device)
+
+    def decide():
+        ds.set(pred=1.0, converged=0.0)          # rho = (1.0 - 0.5) / 1.0 -> accepted: the heavy path
+        lib.tr_decide(ds.sp, ds.wp, loss.data_ptr(), trial_l.data_ptr(), 0, gv.data_ptr(), prev_g.data_ptr(),
+                      old_w.data_ptr(), p.data_ptr(), w.data_ptr(), h.S_ptr, h.Y_ptr, n, h.ld, 0, 0, 0, k, st)
+    calls["dd4ml_tr_decide"] = decide
     out = {}
     for name, fn in calls.items():
         if name == "dd4ml_tr_apply":
@@ -345,6 +352,7 @@ def main():
         ts = [a.elapsed_time(b) for a, b in evs]
         byt = algorithmic_bytes(name, n, kmem)
         native[name] = {"launches_per_step": len(ts) / nprof, "avg_us": 1e3 * sum(ts) / len(ts),
+                        "min_us": 1e3 * min(ts), "median_us": 1e3 * statistics.median(ts), "max_us": 1e3 * max(ts),
                         "total_ms_per_step": sum(ts) / nprof,
                         "achieved_gbs": None if not byt else byt / (sum(ts) / len(ts)) / 1e6}
     dominant = max(native, key=lambda k: native[k]["total_ms_per_step"]) if native else "dd4ml_lssr1_begin"

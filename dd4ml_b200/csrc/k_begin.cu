@@ -145,7 +145,7 @@ extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void*
     { LssrBeginOp<HT_, VT_, WT_, K> op{(dd4ml_state*)state, (const WT_*)w, (WT_*)old_w, (const VT_*)g,       \
           (VT_*)prev_g, (HT_*)S, (HT_*)Y, ld, has_prev, loss, lt};                                           \
       return launch_heavy(op, n, vec, ws, K <= 4 ? 2 : 1,                                                     \
-                          TILE * (int)(2 * sizeof(WT_) + 2 * sizeof(VT_) + 2 * K * sizeof(HT_)), K <= 6, s); }
+                          TILE * (int)(2 * sizeof(WT_) + 2 * sizeof(VT_) + 2 * K * sizeof(HT_)), K <= 4, s); }
 #define CALL(HT, VT, WT) { using HT_ = HT; using VT_ = VT; using WT_ = WT; DD4ML_KCAP_SWITCH(kcap, CALLK) }
     DT_SWITCH3(ht, vt, wt, CALL)
 #undef CALL

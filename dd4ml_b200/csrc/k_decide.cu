@@ -216,7 +216,7 @@ int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* tri
 #define CALLK(K)                                                                                             \
     { DecideOp<HT_, VT_, WT_, K, true> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT_*)g_trial,    \
           (const VT_*)g_old, (VT_*)g_out, (const VT_*)p, (WT_*)w, (HT_*)S, (HT_*)Y, ld};                     \
-      return launch_heavy(op, n, vec, ws, 2, TILE * (int)(3 * sizeof(VT_) + 2 * K * sizeof(HT_)), K <= 6, s); }
+      return launch_heavy(op, n, vec, ws, 2, TILE * (int)(3 * sizeof(VT_) + 2 * K * sizeof(HT_)), K <= 4, s); }
 #define CALL(HT, VT, WT)                                                                                     \
     { using HT_ = HT; using VT_ = VT; using WT_ = WT;                                                        \
       if (!S) { DecideOp<HT, VT, WT, 0, false> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT*)g_trial, \
@@ -235,7 +235,7 @@ int dd4ml_lsr1_update(double* state, double* ws, const void* s_in, const void* y
     const bool vec = aligned16(s_in) && aligned16(y_in) && aligned16(S) && aligned16(Y) && ld % 4 == 0;
 #define CALLK(K)                                                                                             \
     { UpdateOp<HT_, VT_, K> op{(dd4ml_state*)state, (const VT_*)s_in, (const VT_*)y_in, (HT_*)S, (HT_*)Y, ld}; \
-      return launch_heavy(op, n, vec, ws, 2, TILE * (int)(2 * sizeof(VT_) + 2 * K * sizeof(HT_)), K <= 6, s); }
+      return launch_heavy(op, n, vec, ws, 2, TILE * (int)(2 * sizeof(VT_) + 2 * K * sizeof(HT_)), K <= 4, s); }
 #define CALL(HT, VT) { using HT_ = HT; using VT_ = VT; DD4ML_KCAP_SWITCH(kcap, CALLK) }
     DT_SWITCH2(ht, vt, CALL)
 #undef CALL
