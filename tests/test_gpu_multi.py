@@ -27,13 +27,17 @@ def _worker(rank, ws, port, case, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=ws)
-    name, kind, glob, loc, so, dog = case
+    name, kind, glob, loc, so, dog = case[:6]
+    dtype = torch.float64 if "f64" in case[6:] else torch.float32
     g = load_golden(name)
     dev = f"cuda:{rank}"
-    model = FFNN(36, [12, 12], 10)
-    set_flat(model, torch.from_numpy(g["w0"]))
+    model = FFNN(36, [12, 12], 10).to(dtype)
+    set_flat(model, torch.from_numpy(g["w0"]).to(dtype))
     model = model.to(dev)
-    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    if "ddp" in case[6:]:
+        # the reference driver wraps the global model in DDP (trainer_setup.py:187-194)
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[rank])
+    X, Y = torch.from_numpy(g["X"]).to(dtype), torch.from_numpy(g["Y"])
     if kind == "d":
         per = X.shape[0] // ws
         Xr, Yr = X[rank * per:(rank + 1) * per].to(dev), Y[rank * per:(rank + 1) * per].to(dev)
@@ -78,11 +82,13 @@ CASES = [
     ("apts_d_lssr1_so_ws2", "d", "lssr1_tr", "lssr1_tr", True, True),
     ("apts_p_tr_fo_ws2", "p", "tr", "tr", False, False),
     ("apts_p_tr_so_ws2", "p", "tr", "tr", True, False),
+    ("apts_p_tr_fo_ws2_f64", "p", "tr", "tr", False, False, "f64"),
+    ("apts_d_tr_fo_ws2", "d", "tr", "tr", False, False, "ddp"),
 ]
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("case", CASES, ids=["-".join([c[0]] + list(c[6:])) for c in CASES])
 def test_two_rank_apts_matches_reference(case):
     from _helpers import load_golden
     ws = 2
@@ -97,7 +103,7 @@ def test_two_rank_apts_matches_reference(case):
         p.join(timeout=60)
     g = load_golden(case[0])
     assert np.array_equal(outs[0]["w"], outs[1]["w"]), "global model differs between ranks"
-    name, kind, glob, loc, so, dog = case
+    name, kind, glob, loc, so, dog = case[:6]
     if not so:      # first order: the whole trajectory matches the unmodified reference
         np.testing.assert_allclose(outs[0]["loss"], g["loss"], rtol=1e-3)
         np.testing.assert_allclose(outs[0]["delta"], g["delta"], rtol=1e-9)
