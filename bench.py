@@ -194,8 +194,23 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
         out[name] = {"n": n, "k": kk, "ms": ms, "bytes": byt, "achieved": byt / ms / 1e6,
                      "frac": byt / ms / 1e6 / peak_gbs}
     sel = out.get(kernel) or out["dd4ml_lssr1_begin"]
+    # DRAM traffic of the same kernel at the same (n, k) from the committed `ncu --set full` capture
+    traffic = None
+    try:
+        key = {"dd4ml_lssr1_begin": "LssrBeginOp", "dd4ml_tr_propose": "ProposeOp", "dd4ml_tr_apply": "ApplyOp",
+               "dd4ml_lssr1_eval": "EvalOp", "dd4ml_lssr1_trial": "TrialOp"}[kernel if kernel in out else "dd4ml_lssr1_begin"]
+        summ = json.load(open(os.path.join(ROOT, "profiles", "ncu_full_r1_summary.json")))[key]
+        unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tr = 0.0
+        for f in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = summ[f].split()
+            tr += float(v) * unit[u]
+        if n == 1 << 26 and k == 3:
+            traffic = tr
+    except Exception:  # noqa: BLE001
+        traffic = None
     roof = {"bound": "hbm", "achieved": sel["achieved"], "peak": peak_gbs, "unit": "GB/s",
-            "frac": sel["frac"], "traffic": None, "kernel": kernel if kernel in out else "dd4ml_lssr1_begin",
+            "frac": sel["frac"], "traffic": traffic, "kernel": kernel if kernel in out else "dd4ml_lssr1_begin",
             "workload": f"fp32 n=2^26 k={sel['k']} (inputs >> L2)", "peak_source": peak_src,
             "bytes_per_launch": sel["bytes"], "ms_per_launch": sel["ms"]}
     return roof, out
