@@ -173,7 +173,7 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
     def decide():
         ds.set(pred=1.0, converged=0.0)          # rho = (1.0 - 0.5) / 1.0 -> accepted: the heavy path
         lib.tr_decide(ds.sp, ds.wp, loss.data_ptr(), trial_l.data_ptr(), 0, gv.data_ptr(), prev_g.data_ptr(),
-                      old_w.data_ptr(), p.data_ptr(), w.data_ptr(), h.S_ptr, h.Y_ptr, n, h.ld, 0, 0, 0, k, st)
+                      old_w.data_ptr(), p.data_ptr(), w.data_ptr(), h.S_ptr, h.Y_ptr, None, n, h.ld, 0, 0, 0, k, st)
     calls["dd4ml_tr_decide"] = decide
     out = {}
     for name, fn in calls.items():

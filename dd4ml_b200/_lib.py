@@ -57,7 +57,8 @@ _SIGS = {
     "dd4ml_state_set": ([c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_double), c_void_p], c_int),
     "dd4ml_tr_propose": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p], c_int),
     "dd4ml_tr_apply": ([c_void_p] * 7 + [c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p], c_int),
-    "dd4ml_tr_decide": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 7 + [c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "dd4ml_tr_decide": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p], c_int),
+    "dd4ml_state_link": ([c_void_p, c_int, c_void_p, c_int, c_double, c_double, c_double, c_void_p], c_int),
     "dd4ml_lsr1_update": ([c_void_p] * 6 + [c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
     "dd4ml_lsr1_B": ([c_void_p] * 6 + [c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
     "dd4ml_lssr1_begin": ([c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p], c_int),

@@ -21,6 +21,8 @@ struct DecideOp {
     HT* S;
     HT* Y;
     int64_t ld;
+    void* loss_out;      // nullable: device-side select of the returned loss (sync-free TR)
+    int copy_old;        // rejected/converged: g_out <- g_old (only needed when they are different buffers)
     Slots<KMAX> sl;
     bool accept, conv;
     double rho, f0, f1;
@@ -36,7 +38,7 @@ struct DecideOp {
         accept = (lt == 0) ? ks::tr_accept<float>(f0, f1, st->pred[0], st->tol[0], st->nu_dec[0], &rho)
                            : ks::tr_accept<double>(f0, f1, st->pred[0], st->tol[0], st->nu_dec[0], &rho);
     }
-    __device__ bool active() const { return !conv; }
+    __device__ bool active() const { return !conv || copy_old; }
     __device__ bool use_tma() const { return accept; }
     __device__ void stream_desc(int s, const void*& q, int& esz) const {
         esz = (int)sizeof(VT);
@@ -52,13 +54,20 @@ struct DecideOp {
     __device__ __forceinline__ void body_l(const L& l, int64_t i, double* acc) {
         Raw<V, VT> prw;
         if (!accept) {  // tr.py:216 undo (always register staged)
-            Raw<V, WT> wr;
-            ldr_ro<V, VT>(prw, p, i);
-            ldr_rw<V, WT>(wr, w, i);
-            double wv[V];
+            if (!conv) {
+                Raw<V, WT> wr;
+                ldr_ro<V, VT>(prw, p, i);
+                ldr_rw<V, WT>(wr, w, i);
+                double wv[V];
 #pragma unroll
-            for (int e = 0; e < V; ++e) wv[e] = (double)wr.x[e] - (double)prw.x[e];
-            st_v<V, WT>(w, i, wv);
+                for (int e = 0; e < V; ++e) wv[e] = (double)wr.x[e] - (double)prw.x[e];
+                st_v<V, WT>(w, i, wv);
+            }
+            if (copy_old) {
+                double ov[V];
+                ld_ro<V, VT>(go, i, ov);
+                st_v<V, VT>(gout, i, ov);
+            }
             return;
         }
         Raw<V, VT> tr, orw;
@@ -104,6 +113,7 @@ struct DecideOp {
     __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
         t->loss[0] = f0;
         t->trial_loss[0] = f1;
+        if (loss_out != nullptr) st_scalar(loss_out, lt, accept ? f1 : f0);
         if (conv) {  // tr.py:147: nothing happened
             t->accept[0] = 0.0;
             t->out_gn[0] = t->gn[0];
@@ -206,21 +216,23 @@ extern "C" {
 
 int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* trial_loss, int lt,
                     const void* g_trial, const void* g_old, void* g_out, const void* p, void* w,
-                    void* S, void* Y, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream) {
+                    void* S, void* Y, void* loss_out, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap,
+                    void* stream) {
     if (!state || !ws || !loss || !trial_loss || !g_trial || !g_old || !g_out || !p || !w || n < 0 || kcap > DD4ML_MAXM)
         return DD4ML_E_ARG;
     if (lt != 0 && lt != 1) return DD4ML_E_DTYPE;
     cudaStream_t s = (cudaStream_t)stream;
+    const int copy_old = (loss_out != nullptr && g_old != g_out) ? 1 : 0;   // device-side select mode only
     const bool vec = aligned16(g_trial) && aligned16(g_old) && aligned16(g_out) && aligned16(p) && aligned16(w) &&
                      (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
 #define CALLK(K)                                                                                             \
     { DecideOp<HT_, VT_, WT_, K, true> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT_*)g_trial,    \
-          (const VT_*)g_old, (VT_*)g_out, (const VT_*)p, (WT_*)w, (HT_*)S, (HT_*)Y, ld};                     \
+          (const VT_*)g_old, (VT_*)g_out, (const VT_*)p, (WT_*)w, (HT_*)S, (HT_*)Y, ld, loss_out, copy_old};                     \
       return launch_heavy(op, n, vec, ws, 2, TILE * (int)(3 * sizeof(VT_) + 2 * K * sizeof(HT_)), K <= 4, s); }
 #define CALL(HT, VT, WT)                                                                                     \
     { using HT_ = HT; using VT_ = VT; using WT_ = WT;                                                        \
       if (!S) { DecideOp<HT, VT, WT, 0, false> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT*)g_trial, \
-                    (const VT*)g_old, (VT*)g_out, (const VT*)p, (WT*)w, nullptr, nullptr, ld};               \
+                    (const VT*)g_old, (VT*)g_out, (const VT*)p, (WT*)w, nullptr, nullptr, ld, loss_out, copy_old};               \
                 return launch(op, n, vec, ws, 4, s); }                                                       \
       DD4ML_KCAP_SWITCH(kcap, CALLK) }
     DT_SWITCH3(ht, vt, wt, CALL)

@@ -51,6 +51,15 @@ __global__ void state_init_kernel(double* st, int nst, double* ws, int nws) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nst; i += gridDim.x * blockDim.x) st[i] = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nws; i += gridDim.x * blockDim.x) ws[i] = 0.0;
 }
+// dst[dst_off] = clamp(src[src_off] * scale, lo, hi): radius bookkeeping between optimizer state
+// blocks (apts_base.py:228-237, apts_p.py:169,236) without a host round trip
+__global__ void state_link_kernel(double* dst, int dst_off, const double* src, int src_off, double scale, double lo,
+                                  double hi) {
+    double v = src[src_off] * scale;
+    v = v < lo ? lo : v;
+    v = v > hi ? hi : v;
+    dst[dst_off] = v;
+}
 __global__ void state_defaults_kernel(dd4ml_state* st, double gamma0) {
     st->gamma[0] = gamma0;
     st->spare[0] = 0.0;
@@ -105,6 +114,14 @@ int dd4ml_state_set(double* state, int count, const int* offsets, const double* 
         tb.val[i] = values[i];
     }
     state_set_kernel<<<1, SET_MAX, 0, (cudaStream_t)stream>>>(state, tb);
+    return (int)cudaGetLastError();
+}
+
+int dd4ml_state_link(double* dst, int dst_off, const double* src, int src_off, double scale, double lo, double hi,
+                     void* stream) {
+    const int nst = dd4ml_state_doubles();
+    if (!dst || !src || dst_off < 0 || dst_off >= nst || src_off < 0 || src_off >= nst) return DD4ML_E_ARG;
+    state_link_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dst, dst_off, src, src_off, scale, lo, hi);
     return (int)cudaGetLastError();
 }
 

@@ -14,6 +14,7 @@ Device-side design:
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -95,6 +96,23 @@ class APTS_Base(Optimizer):
         # CUDA-graph replay of the (untouched) PyTorch forward/backward of the closures
         self._glob_eval = None if self._is_ddp else GraphedEval(self.model, self.criterion, self._gfs)
         self._loc_eval = None          # created by the subclass once the local model exists
+        self._device_control = False   # see _enable_device_control
+
+    def _enable_device_control(self):
+        """TR/TR configurations run an outer iteration with ONE host read at its end: the inner TR
+        steps, the control step and the radius hand-over between the APTS / global / local state
+        blocks all stay on the device (DD4ML_B200_DEVICE_CONTROL=0 restores one read per step)."""
+        on = (os.environ.get("DD4ML_B200_DEVICE_CONTROL", "1") != "0" and type(self.glob_opt) is TR
+              and type(self.loc_opt) is TR and self.glob_opt._flat_params_fn is None
+              and self.loc_opt._flat_params_fn is None)
+        self._device_control = on
+        self.glob_opt.device_control = on if type(self.glob_opt) is TR else False
+        self.loc_opt.device_control = on if type(self.loc_opt) is TR else False
+
+    def _link(self, dst, src, scale=1.0, lo=-math.inf, hi=math.inf):
+        """dst.delta <- clamp(src.delta * scale, lo, hi) on the device."""
+        off = self._ctl.lay.off("delta")
+        self._ctl.lib.state_link(dst.sp, off, src.sp, off, float(scale), float(lo), float(hi), _lib.stream())
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self):
@@ -220,6 +238,8 @@ class APTS_Base(Optimizer):
             raise ValueError("Closure must be provided for global/local optimization step in APTS.")
         for _ in range(max_iters):
             loss, grad = optim.step(closure=closure, loss=loss, grad=grad)
+            if getattr(optim, "device_control", False):
+                continue        # converged steps are predicated no-ops on the device
             if hasattr(optim, "tol") and self._grad_norm_of(optim, grad) <= optim.tol:
                 break
         return loss, grad
@@ -252,7 +272,12 @@ class APTS_Base(Optimizer):
         lib.apts_control(ctl.sp, ctl.wp, _lib.ptr(f0), _lib.ptr(trial), _lib.dt(f0.dtype), pred_ptr, pred_dt,
                          _lib.ptr(self._gfs.data), _lib.ptr(b["w0"]), _lib.ptr(b["g0"]), _lib.ptr(G),
                          _lib.ptr(out), aux_ptr, n, _lib.dt(b["g0"].dtype), wt, st)
-        rep = ctl.read()
+        if self._device_control:
+            return out, b["g0"], None, None, None
+        return (out, b["g0"]) + self._read_control()
+
+    def _read_control(self):
+        rep = self._ctl.read()
         self.delta = rep.delta
         self._ctl_pushed["delta"] = float(rep.delta)
         self.update_pytorch_lr()
@@ -260,7 +285,7 @@ class APTS_Base(Optimizer):
         gn = None
         if rep.accept != 0.0:
             gn = rep.out_ginf if self.norm_type == math.inf else math.sqrt(rep.out_gg)
-        return out, b["g0"], rep.delta, rep.aux, gn
+        return rep.delta, rep.aux, gn
 
     def control_step(self, step: torch.Tensor, pred: torch.Tensor | None = None, closure=None):
         """Public form of apts_base.py:432-501 (``pred`` must be supplied; the pred=None branch is

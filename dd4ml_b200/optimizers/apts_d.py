@@ -58,19 +58,26 @@ class APTS_D(APTS_Base):
             self.glob_opt.delta = min(self.glob_opt.max_delta, self.delta * self.sqrt_n_global)
             self.loc_opt.delta = min(self.loc_opt.max_delta, self.delta * self.sqrt_n_local)
         self._has_buffers = any(True for _ in self.loc_model.buffers())
+        self._enable_device_control()
         from ..graphs import GraphedEval
         self._loc_eval = GraphedEval(self.loc_model, self.criterion, self._lfs)
 
     # ------------------------------------------------------------------ apts_base.py:228-243
     @torch.no_grad()
     def sync_glob_to_loc(self):
-        self.delta = self.glob_opt.delta
-        self.update_pytorch_lr()
-        self.loc_opt.delta = self.glob_opt.delta
-        if self.norm_type == 2 and self.nr_models > 1:
-            self.loc_opt.delta /= self.nr_models
-        if hasattr(self.loc_opt, "update_pytorch_lr"):
-            self.loc_opt.update_pytorch_lr()
+        if self._device_control:        # radii handed over on the device, read once at the end of step()
+            scale = 1.0 / self.nr_models if (self.norm_type == 2 and self.nr_models > 1) else 1.0
+            self._link(self._ctl, self.glob_opt._ds)
+            self._link(self.loc_opt._ds, self.glob_opt._ds, scale)
+            self.loc_opt._delta_stale = True
+        else:
+            self.delta = self.glob_opt.delta
+            self.update_pytorch_lr()
+            self.loc_opt.delta = self.glob_opt.delta
+            if self.norm_type == 2 and self.nr_models > 1:
+                self.loc_opt.delta /= self.nr_models
+            if hasattr(self.loc_opt, "update_pytorch_lr"):
+                self.loc_opt.update_pytorch_lr()
         # load_state_dict(global) as ONE flat device copy (+ module buffers such as BatchNorm stats)
         if self._gfs.ensure() | self._lfs.ensure():
             self._buffers()
@@ -144,12 +151,20 @@ class APTS_D(APTS_Base):
         loss, grad, delta, evals_sum, gn = self._control(
             comm, 0, scale, 0.0, self.init_glob_loss, comm.data_ptr() + n * es, wt,
             comm.data_ptr() + (n + 1) * es)
+        if self._device_control:
+            self._link(self.glob_opt._ds, self._ctl)                  # glob_opt.delta <- control delta
+            self.glob_opt._delta_stale = True
+            if self.glob_pass:
+                loss, grad = self.glob_steps(loss, grad)
+            self.sync_glob_to_loc()
+            delta, evals_sum, gn = self._read_control()               # the only host read of the iteration
+        else:
+            self.glob_opt.delta = delta
+            if self.glob_pass:
+                self.glob_opt._known_gn = None if gn is None else (id(grad), grad._version, grad.data_ptr(), gn)
+                loss, grad = self.glob_steps(loss, grad)
+            self.sync_glob_to_loc()
         self.grad_evals += evals_sum / (self.nr_models if self._distributed else 1)   # apts_base.py:413-417
-        self.glob_opt.delta = delta
-        if self.glob_pass:
-            self.glob_opt._known_gn = None if gn is None else (id(grad), grad._version, grad.data_ptr(), gn)
-            loss, grad = self.glob_steps(loss, grad)
-        self.sync_glob_to_loc()
         return loss
 
     def step(self, inputs, labels, inputs_d=None, labels_d=None, hNk=None):

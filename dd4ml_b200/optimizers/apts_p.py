@@ -77,6 +77,7 @@ class APTS_P(APTS_Base):
         self._seg_all = (len(order), mk([loff[t] for t in order]), mk([goff[t] for t in order]),
                          mk([numel[t] for t in order]))
         self._has_buffers = any(True for _ in self.loc_model.buffers())
+        self._enable_device_control()
         from ..graphs import GraphedEval
         self._loc_eval = GraphedEval(self.loc_model, self.criterion, self._lfs)
 
@@ -112,11 +113,16 @@ class APTS_P(APTS_Base):
     # ------------------------------------------------------------------ apts_p.py:167-180
     @torch.no_grad()
     def sync_glob_to_loc(self):
-        self.delta = min(self.max_delta, max(self.min_delta, self.glob_opt.delta / self.sqrt_n_global))
-        self.update_pytorch_lr()
-        self.loc_opt.delta = self.glob_opt.delta
-        if hasattr(self.loc_opt, "update_pytorch_lr"):
-            self.loc_opt.update_pytorch_lr()
+        if self._device_control:
+            self._link(self._ctl, self.glob_opt._ds, 1.0 / self.sqrt_n_global, self.min_delta, self.max_delta)
+            self._link(self.loc_opt._ds, self.glob_opt._ds)
+            self.loc_opt._delta_stale = True
+        else:
+            self.delta = min(self.max_delta, max(self.min_delta, self.glob_opt.delta / self.sqrt_n_global))
+            self.update_pytorch_lr()
+            self.loc_opt.delta = self.glob_opt.delta
+            if hasattr(self.loc_opt, "update_pytorch_lr"):
+                self.loc_opt.update_pytorch_lr()
         cnt, dsto, srco, lens = self._seg_all
         self._ctl.lib.seg_copy(_lib.ptr(self._lfb.data), _lib.ptr(self._gfs.data), cnt, dsto, srco, lens,
                                self._lfb.n, 0, _lib.dt(self._gfs.dtype), _lib.stream())
@@ -157,11 +163,19 @@ class APTS_P(APTS_Base):
         loss, grad, new_delta, evals_sum, gn = self._control(
             comm, 1, 1.0, self.delta, self.init_glob_loss, comm.data_ptr() + n * es, _lib.dt(comm.dtype),
             comm.data_ptr() + (n + 1) * es)
+        if self._device_control:
+            self._link(self.glob_opt._ds, self._ctl, self.sqrt_n_global, hi=self.glob_opt.max_delta)
+            self.glob_opt._delta_stale = True
+            if self.glob_pass:
+                loss, grad = self.glob_steps(loss, grad)
+            self.sync_glob_to_loc()
+            new_delta, evals_sum, gn = self._read_control()           # the only host read of the iteration
+        else:
+            self.delta = new_delta
+            self.glob_opt.delta = min(self.glob_opt.max_delta, new_delta * self.sqrt_n_global)
+            if self.glob_pass:
+                self.glob_opt._known_gn = None if gn is None else (id(grad), grad._version, grad.data_ptr(), gn)
+                loss, grad = self.glob_steps(loss, grad)
+            self.sync_glob_to_loc()
         self.grad_evals += evals_sum / (self.nr_models if self._distributed else 1)
-        self.delta = new_delta
-        self.glob_opt.delta = min(self.glob_opt.max_delta, new_delta * self.sqrt_n_global)
-        if self.glob_pass:
-            self.glob_opt._known_gn = None if gn is None else (id(grad), grad._version, grad.data_ptr(), gn)
-            loss, grad = self.glob_steps(loss, grad)
-        self.sync_glob_to_loc()
         return loss

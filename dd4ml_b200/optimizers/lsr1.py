@@ -96,8 +96,11 @@ class LSR1:
         """Refresh the host mirrors from a report the owner just read."""
         self._k_host = int(rep.k)
         self._gamma_host = float(rep.gamma)
+        self._stale = False
 
     def num_pairs(self) -> int:
+        if getattr(self, "_stale", False):      # device-control mode: mirrors are refreshed on demand
+            self.absorb(self.ds.read())
         return self._k_host
 
     def _order(self):
@@ -107,6 +110,8 @@ class LSR1:
 
     @property
     def gamma(self) -> torch.Tensor:
+        if getattr(self, "_stale", False):
+            self.absorb(self.ds.read())
         return torch.tensor(self._gamma_host, dtype=self.dtype, device=self.device)
 
     @gamma.setter

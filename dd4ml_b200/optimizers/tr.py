@@ -43,6 +43,20 @@ def as_device_scalar(x, device, like_dtype=torch.float32) -> torch.Tensor:
 class TR(Optimizer):
     __name__ = "TR"
 
+    # `delta` lives in the device state block; the host attribute is a lazily refreshed mirror.  In
+    # device-control mode a step does not read anything back, so reading `opt.delta` afterwards costs
+    # one report read (the reference keeps it as a python float, tr.py:33).
+    @property
+    def delta(self):
+        if getattr(self, "_delta_stale", False):
+            self._absorb(self._ds.read())
+        return self._delta
+
+    @delta.setter
+    def delta(self, value):
+        self._delta = value
+        self._delta_stale = False
+
     @staticmethod
     def setup_TR_hparams(cfg):
         for k, v in get_tr_hparams(cfg).items():
@@ -70,6 +84,9 @@ class TR(Optimizer):
             raise _lib.DD4MLError("dd4ml_b200 TR supports norm_type 2 and inf")
         self._flat_grads_fn = flat_grads_fn
         self._flat_params_fn = flat_params_fn
+        # sync-free mode (north star: ratio test and radius update on the device, no host sync per
+        # inner iteration): set by the APTS classes, or TR(..., device_control=True)
+        self.device_control = bool(kwargs.pop("device_control", False))
 
         super().__init__(params, {"lr": self.delta})
         self.ps = [p for g in self.param_groups for p in g["params"]]
@@ -109,8 +126,18 @@ class TR(Optimizer):
         for g in self.param_groups:
             g["lr"] = self.delta
 
+    def _absorb(self, rep):
+        """Refresh the host mirrors from a report read."""
+        self._delta = rep.delta
+        self._delta_stale = False
+        self._pushed["delta"] = float(rep.delta)
+        self._step_norm_cache = rep.pnorm
+        self.last_report = rep
+        if self.hess is not None:
+            self.hess.absorb(rep)
+
     def _push_hparams(self):
-        cur = {k: float(getattr(self, k)) for k in _HP}
+        cur = {k: float(getattr(self, k)) for k in _HP if not (k == "delta" and getattr(self, "_delta_stale", False))}
         diff = {k: v for k, v in cur.items() if self._pushed.get(k) != v}
         if diff:
             self._ds.set(**diff)
@@ -196,6 +223,9 @@ class TR(Optimizer):
         kcap = self.mem_length if h is not None else 0
         vtc, wtc = _lib.dt(vt), _lib.dt(w.dtype)
 
+        if self.device_control and self._flat_params_fn is None:
+            return self._step_device(closure, loss, loss_t, grad, w, b, S, Y, n, ld, vtc, ht, wtc, kcap, st)
+
         lib.tr_propose(ds.sp, ds.wp, _lib.ptr(grad), S, Y, n, ld, vtc, ht, 0, kcap, st)
         # convergence test (tr.py:147): ||g|| is already known on the host when `grad` is the
         # vector this optimizer returned last time; otherwise one extra report read.
@@ -222,16 +252,11 @@ class TR(Optimizer):
         G = self._current_grad(vt)
         g_out = b["g_out"]
         lib.tr_decide(ds.sp, ds.wp, _lib.ptr(loss_t), _lib.ptr(trial_t), _lib.dt(loss_t.dtype), _lib.ptr(G),
-                      _lib.ptr(grad), _lib.ptr(g_out), _lib.ptr(self._step_buf), _lib.ptr(w), S, Y, n, ld,
+                      _lib.ptr(grad), _lib.ptr(g_out), _lib.ptr(self._step_buf), _lib.ptr(w), S, Y, None, n, ld,
                       vtc, ht, wtc, kcap, st)
         rep = ds.read()
         DeviceState.raise_for(rep.err)
-        self.last_report = rep
-        self.delta = rep.delta
-        self._pushed["delta"] = float(rep.delta)
-        self._step_norm_cache = rep.pnorm
-        if h is not None:
-            h.absorb(rep)
+        self._absorb(rep)
         self.update_pytorch_lr()
         accepted = rep.accept != 0.0
         if self._flat_params_fn is not None and not accepted:
@@ -240,6 +265,44 @@ class TR(Optimizer):
         self._known_gn = (id(out_grad), out_grad._version, out_grad.data_ptr(), rep.out_gn)
         self.last_grad_norm = rep.out_gn
         return out_loss, out_grad
+
+    def _step_device(self, closure, loss, loss_t, grad, w, b, S, Y, n, ld, vtc, ht, wtc, kcap, st):
+        """One TR iteration without any host read-back: the convergence test, the ratio test, the
+        accept/undo, the L-SR1 update and the radius update are all predicated on device state, and
+        the returned (loss, gradient) are selected on the device.  Differences from tr.py:138-222:
+        when ||g|| <= tol the closure is still evaluated once (at the unchanged point) and numerical
+        failures (state.err) surface at the next report read instead of inside this call."""
+        lib, ds = self._ds.lib, self._ds
+        self._step_buf = b["step"]
+        lib.tr_propose(ds.sp, ds.wp, _lib.ptr(grad), S, Y, n, ld, vtc, ht, 0, kcap, st)
+        lib.tr_apply(ds.sp, ds.wp, _lib.ptr(grad), S, Y, _lib.ptr(self._step_buf), _lib.ptr(w), n, ld,
+                     vtc, ht, wtc, kcap, st)
+        trial_loss = closure(compute_grad=True)
+        trial_t = as_device_scalar(trial_loss, self._fs.device, loss_t.dtype)
+        if trial_t.dtype != loss_t.dtype:
+            trial_t = trial_t.to(loss_t.dtype)
+        G = self._current_grad(b["step"].dtype)
+        g_out = b["g_out"]
+        lo = b.get("loss_out")
+        if lo is None or lo.dtype != loss_t.dtype:
+            lo = b["loss_out"] = torch.empty((), dtype=loss_t.dtype, device=self._fs.device)
+        lib.tr_decide(ds.sp, ds.wp, _lib.ptr(loss_t), _lib.ptr(trial_t), _lib.dt(loss_t.dtype), _lib.ptr(G),
+                      _lib.ptr(grad), _lib.ptr(g_out), _lib.ptr(self._step_buf), _lib.ptr(w), S, Y, _lib.ptr(lo),
+                      n, ld, vtc, ht, wtc, kcap, st)
+        self._delta_stale = True
+        if self.hess is not None:
+            self.hess._stale = True
+        self._known_gn = None
+        self.last_grad_norm = None
+        return lo, g_out
+
+    def sync(self):
+        """Read the report block once (device-control mode): refreshes delta / L-SR1 mirrors and raises
+        pending numerical errors."""
+        rep = self._ds.read()
+        DeviceState.raise_for(rep.err)
+        self._absorb(rep)
+        return rep
 
     # ------------------------------------------------------------------ checkpointing (SURVEY §8f)
     def state_dict(self):

@@ -48,6 +48,10 @@ int dd4ml_max_mem_length(void);
 int dd4ml_state_init(double* state, double* ws, double gamma0, void* stream);
 /* state[offsets[i]] = values[i], i < count <= 32 (hyper-parameters, delta written by the host) */
 int dd4ml_state_set(double* state, int count, const int* offsets, const double* values, void* stream);
+/* dst[dst_off] = clamp(src[src_off] * scale, lo, hi): radius hand-over between the APTS, global and local
+ * optimizer state blocks on the device (apts_base.py:228-237, apts_d.py:202, apts_p.py:169,236) */
+int dd4ml_state_link(double* dst, int dst_off, const double* src, int src_off, double scale, double lo, double hi,
+                     void* stream);
 
 /* ---- TR.step, optimizers/tr.py:138-222 -------------------------------------------------
  * propose: ||g|| (2 or inf), S^T g, Y^T g in one pass; the last CTA then solves the
@@ -57,14 +61,18 @@ int dd4ml_state_set(double* state, int count, const int* offsets, const double* 
  * apply:   p = cg*g + sum_j cS_j S_j + cY_j Y_j;  optionally w += p  (tr.py:106-131,179).
  * decide:  rho test (tr.py:186-191); accepted: y = g_trial - g_old, candidate pair
  *   reductions, g_out <- g_trial, L-SR1 update chain + radius update in the last CTA
- *   (lsr1.py:53-144, tr.py:193-214); rejected: w -= p, radius shrink (tr.py:216-222). */
+ *   (lsr1.py:53-144, tr.py:193-214); rejected: w -= p, radius shrink (tr.py:216-222).
+ *   loss_out (nullable): device-side select of what TR.step returns -- loss_out <- accepted ?
+ *   trial_loss : loss and, when g_out != g_old, g_out <- g_old on rejection -- so the host needs no
+ *   read-back per inner iteration. */
 int dd4ml_tr_propose(double* state, double* ws, const void* g, const void* S, const void* Y,
                      int64_t n, int64_t ld, int vt, int ht, int mode, int kcap, void* stream);
 int dd4ml_tr_apply(double* state, double* ws, const void* g, const void* S, const void* Y, void* p,
                    void* w, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream);
 int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* trial_loss, int lt,
                     const void* g_trial, const void* g_old, void* g_out, const void* p, void* w,
-                    void* S, void* Y, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream);
+                    void* S, void* Y, void* loss_out, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap,
+                    void* stream);
 
 /* ---- LSSR1_TR.step, optimizers/lssr1_tr.py:493-654 --------------------------------------
  * begin: s = w - old_w, y = g - prev_g (lssr1_tr.py:518-526) with every reduction of the

@@ -222,11 +222,17 @@ def _apts(kind, model, glob, loc, c, **extra):
                max_glob_iters=1, tol=1e-6, **extra, **c.apts_params)
 
 
-def test_apts_d_single_rank_matches_reference():
+@pytest.mark.parametrize("device_control", ["1", "0"])
+def test_apts_d_single_rank_matches_reference(device_control, monkeypatch):
+    """device_control=1: one host read per OUTER iteration (TR steps, control step and radius hand-over
+    stay on the device); 0: one read per TR step.  Both reproduce the reference golden."""
+    monkeypatch.setenv("DD4ML_B200_DEVICE_CONTROL", device_control)
     g = load_golden("apts_d_tr_fo_ws1")
     X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
     model = gpu_model(g)
     opt = _apts("d", model, "tr", "tr", cfg(), foc=True)
+    assert opt._device_control == (device_control == "1")
+    syncs0 = opt._ctl.syncs + opt.glob_opt._ds.syncs + opt.loc_opt._ds.syncs
     losses, deltas, gev = [], [], []
     for i in range(int(g["steps"])):
         losses.append(float(opt.step(X, Y)))
@@ -237,6 +243,9 @@ def test_apts_d_single_rank_matches_reference():
     np.testing.assert_allclose(deltas, g["delta"], rtol=1e-9)
     np.testing.assert_allclose(gev, g["grad_evals"], atol=1e-9)
     assert rel_err(flat_of(model), g["w_final"]) < 5e-3
+    syncs = opt._ctl.syncs + opt.glob_opt._ds.syncs + opt.loc_opt._ds.syncs - syncs0
+    if device_control == "1":
+        assert syncs == int(g["steps"])          # exactly one report read per outer iteration
     # local clone equals the global model after the sync
     assert torch.equal(flat_of(opt.loc_model), flat_of(model))
 
