@@ -330,9 +330,12 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0, s0 = lib.launches, opt._ctl.syncs
+    def sync_count():
+        return opt._ctl.syncs + opt.glob_opt._ds.syncs + opt.loc_opt._ds.syncs
+    l0, s0 = lib.launches, sync_count()
     ms, wall = timed_region(step_resident, args.steps, world, device, flush)
     launches = lib.launches - l0
+    host_syncs = (sync_count() - s0) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     value = world * args.steps / (ms / 1e3)
 
@@ -402,7 +405,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "outer_iters_per_sec": args.steps / (ms / 1e3), "wall_ms_per_step": wall * 1e3 / args.steps,
-        "e2e": e2e, "gpu_launches": launches, "host_syncs_per_step": None,
+        "e2e": e2e, "gpu_launches": launches, "host_syncs_per_step": host_syncs,
         "clocks": clocks, "roofline": roofline,
         "roofline_native": {"n": n, "k": kmem, "dominant": dominant, "own_kernel_ms_per_step": own_ms,
                             "own_kernel_share_of_step": own_ms / (ms / args.steps), "kernels": native,

@@ -1,6 +1,6 @@
 """Diagnostics (GPU): k-space cycle counters of the LSSR1 local/global steps of the bench workload."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import build_optimizer, PER_RANK_BATCH
 from dd4ml_b200.workloads import mnist_shape_batch

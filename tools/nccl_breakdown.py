@@ -1,7 +1,7 @@
 """GPU (torchrun, N>=2): cost of torch.distributed all-reduce at the hot path's payload sizes and a
 phase breakdown of one APTS_D outer iteration."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)

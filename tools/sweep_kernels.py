@@ -1,6 +1,6 @@
 """GPU: launch the heavy fused kernels on vectors >> L2 (for ncu captures and quick A/B timing)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import large_n_roofline
 import json
