@@ -80,24 +80,33 @@ struct ApplyOp {
 
 }  // namespace
 
+namespace {
+template <class HT, class VT, class WT>
+int apply_t(double* state, double* ws, const void* g, const void* S, const void* Y, void* p, void* w, int64_t n,
+            int64_t ld, int kcap, bool vec, cudaStream_t s) {
+    constexpr bool FAST = sizeof(HT) == 4 && sizeof(VT) == 4 && sizeof(WT) == 4;
+    if (!S) {
+        ApplyOp<HT, VT, WT, 0> op{(dd4ml_state*)state, (const VT*)g, nullptr, nullptr, (VT*)p, (WT*)w, ld};
+        return launch(op, n, vec, ws, 4, s);
+    }
+    auto run = [&](auto kc) {
+        constexpr int K = decltype(kc)::value;
+        ApplyOp<HT, VT, WT, K> op{(dd4ml_state*)state, (const VT*)g, (const HT*)S, (const HT*)Y, (VT*)p, (WT*)w, ld};
+        return launch_sel<FAST>(op, n, vec, ws, 3, TILE * (int)(sizeof(VT) + sizeof(WT) + 2 * K * sizeof(HT)), K <= 6, s);
+    };
+    DD4ML_RUN_K(FAST, kcap, run)
+}
+}  // namespace
+
 extern "C" int dd4ml_tr_apply(double* state, double* ws, const void* g, const void* S, const void* Y, void* p,
                               void* w, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream) {
     if (!state || !ws || !g || !p || n < 0 || kcap > DD4ML_MAXM) return DD4ML_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = aligned16(g) && aligned16(p) && (!w || aligned16(w)) &&
                      (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
-#define CALLK(K)                                                                                          \
-    { ApplyOp<HT_, VT_, WT_, K> op{(dd4ml_state*)state, (const VT_*)g, (const HT_*)S, (const HT_*)Y, (VT_*)p, \
-                                   (WT_*)w, ld};                                                          \
-      return launch_heavy(op, n, vec, ws, 3, TILE * (int)(sizeof(VT_) + sizeof(WT_) + 2 * K * sizeof(HT_)), K <= 6, s); }
-#define CALL(HT, VT, WT)                                                                                  \
-    { using HT_ = HT; using VT_ = VT; using WT_ = WT;                                                     \
-      if (!S) { ApplyOp<HT, VT, WT, 0> op{(dd4ml_state*)state, (const VT*)g, nullptr, nullptr, (VT*)p, (WT*)w, ld}; \
-                return launch(op, n, vec, ws, 4, s); }                                                    \
-      DD4ML_KCAP_SWITCH(kcap, CALLK) }
+#define CALL(HT, VT, WT) return apply_t<HT, VT, WT>(state, ws, g, S, Y, p, w, n, ld, kcap, vec, s);
     DT_SWITCH3(ht, vt, wt, CALL)
 #undef CALL
-#undef CALLK
 }
 
 extern "C" int dd4ml_tr_propose(double*, double*, const void*, const void*, const void*, int64_t, int64_t, int,

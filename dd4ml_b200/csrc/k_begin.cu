@@ -132,6 +132,22 @@ struct LssrBeginOp {
 
 }  // namespace
 
+namespace {
+template <class HT, class VT, class WT>
+int begin_t(double* state, double* ws, const void* w, void* old_w, const void* g, void* prev_g, int has_prev, void* S,
+            void* Y, const void* loss, int lt, int64_t n, int64_t ld, int kcap, bool vec, cudaStream_t s) {
+    constexpr bool FAST = sizeof(HT) == 4 && sizeof(VT) == 4 && sizeof(WT) == 4;
+    auto run = [&](auto kc) {
+        constexpr int K = decltype(kc)::value;
+        LssrBeginOp<HT, VT, WT, K> op{(dd4ml_state*)state, (const WT*)w, (WT*)old_w, (const VT*)g, (VT*)prev_g,
+                                      (HT*)S, (HT*)Y, ld, has_prev, loss, lt};
+        return launch_sel<FAST>(op, n, vec, ws, K <= 4 ? 2 : 1,
+                                TILE * (int)(2 * sizeof(WT) + 2 * sizeof(VT) + 2 * K * sizeof(HT)), K <= 4, s);
+    };
+    DD4ML_RUN_K(FAST, kcap, run)
+}
+}  // namespace
+
 extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void* old_w, const void* g,
                                  void* prev_g, int has_prev, void* S, void* Y, const void* loss, int lt,
                                  int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream) {
@@ -141,13 +157,8 @@ extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void*
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = aligned16(w) && aligned16(old_w) && aligned16(g) && aligned16(prev_g) && aligned16(S) &&
                      aligned16(Y) && ld % 4 == 0;
-#define CALLK(K)                                                                                             \
-    { LssrBeginOp<HT_, VT_, WT_, K> op{(dd4ml_state*)state, (const WT_*)w, (WT_*)old_w, (const VT_*)g,       \
-          (VT_*)prev_g, (HT_*)S, (HT_*)Y, ld, has_prev, loss, lt};                                           \
-      return launch_heavy(op, n, vec, ws, K <= 4 ? 2 : 1,                                                     \
-                          TILE * (int)(2 * sizeof(WT_) + 2 * sizeof(VT_) + 2 * K * sizeof(HT_)), K <= 4, s); }
-#define CALL(HT, VT, WT) { using HT_ = HT; using VT_ = VT; using WT_ = WT; DD4ML_KCAP_SWITCH(kcap, CALLK) }
+#define CALL(HT, VT, WT) \
+    return begin_t<HT, VT, WT>(state, ws, w, old_w, g, prev_g, has_prev, S, Y, loss, lt, n, ld, kcap, vec, s);
     DT_SWITCH3(ht, vt, wt, CALL)
 #undef CALL
-#undef CALLK
 }

@@ -212,6 +212,39 @@ struct UpdateOp {
 
 }  // namespace
 
+namespace {
+template <class HT, class VT, class WT>
+int decide_t(double* state, double* ws, const void* loss, const void* trial_loss, int lt, const void* g_trial,
+             const void* g_old, void* g_out, const void* p, void* w, void* S, void* Y, void* loss_out, int copy_old,
+             int64_t n, int64_t ld, int kcap, bool vec, cudaStream_t s) {
+    constexpr bool FAST = sizeof(HT) == 4 && sizeof(VT) == 4 && sizeof(WT) == 4;
+    if (!S) {
+        DecideOp<HT, VT, WT, 0, false> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT*)g_trial, (const VT*)g_old,
+                                          (VT*)g_out, (const VT*)p, (WT*)w, nullptr, nullptr, ld, loss_out, copy_old};
+        return launch(op, n, vec, ws, 4, s);
+    }
+    auto run = [&](auto kc) {
+        constexpr int K = decltype(kc)::value;
+        DecideOp<HT, VT, WT, K, true> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT*)g_trial, (const VT*)g_old,
+                                         (VT*)g_out, (const VT*)p, (WT*)w, (HT*)S, (HT*)Y, ld, loss_out, copy_old};
+        return launch_sel<FAST>(op, n, vec, ws, 2, TILE * (int)(3 * sizeof(VT) + 2 * K * sizeof(HT)), K <= 4, s);
+    };
+    DD4ML_RUN_K(FAST, kcap, run)
+}
+
+template <class HT, class VT>
+int update_t(double* state, double* ws, const void* s_in, const void* y_in, void* S, void* Y, int64_t n, int64_t ld,
+             int kcap, bool vec, cudaStream_t s) {
+    constexpr bool FAST = sizeof(HT) == 4 && sizeof(VT) == 4;
+    auto run = [&](auto kc) {
+        constexpr int K = decltype(kc)::value;
+        UpdateOp<HT, VT, K> op{(dd4ml_state*)state, (const VT*)s_in, (const VT*)y_in, (HT*)S, (HT*)Y, ld};
+        return launch_sel<FAST>(op, n, vec, ws, 2, TILE * (int)(2 * sizeof(VT) + 2 * K * sizeof(HT)), K <= 4, s);
+    };
+    DD4ML_RUN_K(FAST, kcap, run)
+}
+}  // namespace
+
 extern "C" {
 
 int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* trial_loss, int lt,
@@ -225,19 +258,11 @@ int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* tri
     const int copy_old = (loss_out != nullptr && g_old != g_out) ? 1 : 0;   // device-side select mode only
     const bool vec = aligned16(g_trial) && aligned16(g_old) && aligned16(g_out) && aligned16(p) && aligned16(w) &&
                      (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
-#define CALLK(K)                                                                                             \
-    { DecideOp<HT_, VT_, WT_, K, true> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT_*)g_trial,    \
-          (const VT_*)g_old, (VT_*)g_out, (const VT_*)p, (WT_*)w, (HT_*)S, (HT_*)Y, ld, loss_out, copy_old};                     \
-      return launch_heavy(op, n, vec, ws, 2, TILE * (int)(3 * sizeof(VT_) + 2 * K * sizeof(HT_)), K <= 4, s); }
-#define CALL(HT, VT, WT)                                                                                     \
-    { using HT_ = HT; using VT_ = VT; using WT_ = WT;                                                        \
-      if (!S) { DecideOp<HT, VT, WT, 0, false> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT*)g_trial, \
-                    (const VT*)g_old, (VT*)g_out, (const VT*)p, (WT*)w, nullptr, nullptr, ld, loss_out, copy_old};               \
-                return launch(op, n, vec, ws, 4, s); }                                                       \
-      DD4ML_KCAP_SWITCH(kcap, CALLK) }
+#define CALL(HT, VT, WT)                                                                                         \
+    return decide_t<HT, VT, WT>(state, ws, loss, trial_loss, lt, g_trial, g_old, g_out, p, w, S, Y, loss_out, copy_old, \
+                                n, ld, kcap, vec, s);
     DT_SWITCH3(ht, vt, wt, CALL)
 #undef CALL
-#undef CALLK
 }
 
 int dd4ml_lsr1_update(double* state, double* ws, const void* s_in, const void* y_in, void* S, void* Y,
@@ -245,13 +270,9 @@ int dd4ml_lsr1_update(double* state, double* ws, const void* s_in, const void* y
     if (!state || !ws || !s_in || !y_in || !S || !Y || n < 0 || kcap > DD4ML_MAXM) return DD4ML_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = aligned16(s_in) && aligned16(y_in) && aligned16(S) && aligned16(Y) && ld % 4 == 0;
-#define CALLK(K)                                                                                             \
-    { UpdateOp<HT_, VT_, K> op{(dd4ml_state*)state, (const VT_*)s_in, (const VT_*)y_in, (HT_*)S, (HT_*)Y, ld}; \
-      return launch_heavy(op, n, vec, ws, 2, TILE * (int)(2 * sizeof(VT_) + 2 * K * sizeof(HT_)), K <= 4, s); }
-#define CALL(HT, VT) { using HT_ = HT; using VT_ = VT; DD4ML_KCAP_SWITCH(kcap, CALLK) }
+#define CALL(HT, VT) return update_t<HT, VT>(state, ws, s_in, y_in, S, Y, n, ld, kcap, vec, s);
     DT_SWITCH2(ht, vt, CALL)
 #undef CALL
-#undef CALLK
 }
 
 }  // extern "C"

@@ -61,20 +61,30 @@ struct ProposeOp {
 
 }  // namespace
 
+namespace {
+template <class HT, class VT>
+int propose_t(double* state, double* ws, const void* g, const void* S, const void* Y, int64_t n, int64_t ld, int mode,
+              int kcap, bool vec, cudaStream_t s) {
+    constexpr bool FAST = sizeof(HT) == 4 && sizeof(VT) == 4;
+    if (!S) {
+        ProposeOp<HT, VT, 0> op{(dd4ml_state*)state, (const VT*)g, nullptr, nullptr, ld, mode};
+        return launch(op, n, vec, ws, 4, s);
+    }
+    auto run = [&](auto kc) {
+        constexpr int K = decltype(kc)::value;
+        ProposeOp<HT, VT, K> op{(dd4ml_state*)state, (const VT*)g, (const HT*)S, (const HT*)Y, ld, mode};
+        return launch_sel<FAST>(op, n, vec, ws, 3, TILE * (int)(sizeof(VT) + 2 * K * sizeof(HT)), false, s);
+    };
+    DD4ML_RUN_K(FAST, kcap, run)
+}
+}  // namespace
+
 extern "C" int dd4ml_tr_propose(double* state, double* ws, const void* g, const void* S, const void* Y,
                                 int64_t n, int64_t ld, int vt, int ht, int mode, int kcap, void* stream) {
     if (!state || !ws || !g || n < 0 || kcap > DD4ML_MAXM) return DD4ML_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = aligned16(g) && (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
-#define CALLK(K)                                                                                        \
-    { ProposeOp<HT_, VT_, K> op{(dd4ml_state*)state, (const VT_*)g, (const HT_*)S, (const HT_*)Y, ld, mode}; \
-      return launch_heavy(op, n, vec, ws, 3, TILE * (int)(sizeof(VT_) + 2 * K * sizeof(HT_)), false, s); }
-#define CALL(HT, VT)                                                                                    \
-    { using HT_ = HT; using VT_ = VT;                                                                   \
-      if (!S) { ProposeOp<HT, VT, 0> op{(dd4ml_state*)state, (const VT*)g, nullptr, nullptr, ld, mode}; \
-                return launch(op, n, vec, ws, 4, s); }                                                  \
-      DD4ML_KCAP_SWITCH(kcap, CALLK) }
+#define CALL(HT, VT) return propose_t<HT, VT>(state, ws, g, S, Y, n, ld, mode, kcap, vec, s);
     DT_SWITCH2(ht, vt, CALL)
 #undef CALL
-#undef CALLK
 }

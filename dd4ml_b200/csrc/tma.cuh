@@ -11,6 +11,8 @@
 #pragma once
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "heavy.cuh"
 
 namespace {
@@ -194,5 +196,25 @@ inline int launch_heavy(Op op, int64_t n, bool vec, double* ws, int per_sm, int 
     tma_kernel<Op><<<grid, TMA_THREADS, (size_t)nstage * stage_bytes, s>>>(op, n, ws, nstage, stage_bytes);
     return (int)cudaGetLastError();
 }
+
+// FAST = all-fp32 operands: TMA + register-staged variants for KMAX 4/6/8.  The mixed / fp64
+// combinations (rare: PINN runs in float64) only get the register-staged KMAX = 8 kernel, which
+// keeps the build small.
+template <bool FAST, class Op>
+inline int launch_sel(Op op, int64_t n, bool vec, double* ws, int per_sm, int stage_bytes, bool tma_default,
+                      cudaStream_t s) {
+    if constexpr (FAST) return launch_heavy(op, n, vec, ws, per_sm, stage_bytes, tma_default, s);
+    else return launch(op, n, vec, ws, per_sm, s);
+}
+
+template <int K> using KC = std::integral_constant<int, K>;
+
+// calls run(KC<4|6|8>) for FAST combinations, run(KC<8>) otherwise
+#define DD4ML_RUN_K(FAST, kcap, run)                           \
+    if constexpr (FAST) {                                      \
+        if ((kcap) <= 4) return run(KC<4>{});                  \
+        if ((kcap) <= 6) return run(KC<6>{});                  \
+    }                                                          \
+    return run(KC<8>{});
 
 }  // namespace

@@ -318,3 +318,28 @@ def test_optimizers_refuse_cpu_parameters():
     model = nn.Linear(3, 2)
     with pytest.raises(dd4ml_b200.DD4MLError):
         TR(model.parameters(), **get_tr_hparams(cfg()))
+
+
+@pytest.mark.parametrize("so", [False, True])
+def test_tr_float64_parameters_fp32_gradient_buffer(so):
+    """Trainer-style PINN runs call model.double(); the reference TR keeps an fp32 gradient buffer and
+    fp32 L-SR1 pairs while the parameters are fp64 (tr.py:69,76-78): dtype combo (ht, vt, wt) =
+    (f32, f32, f64)."""
+    g = load_golden("tr_fo")
+    X, Y = torch.from_numpy(g["X"]).double(), torch.from_numpy(g["Y"])
+    model = gpu_model(g, dtype=torch.float64)
+    hp = get_tr_hparams(cfg(delta=0.1, min_delta=1e-3, max_delta=2.0, glob_second_order=so))
+    opt = TR(model.parameters(), **hp)
+    closure = make_closure(opt, model, X.to(DEV), Y.to(DEV))
+    ohp = oracle.tr_hparams(0.1, 1e-3, 2.0, second_order=so)
+
+    def orun(eps, seed):
+        gen = torch.Generator().manual_seed(seed)
+        o = oracle.TROracle(**ohp, eig_sign="canonical")
+        fg = noisy_fg(make_fg(FFNN(IN_F, HID, OUT).double(), X, Y), eps, gen)
+        w = torch.from_numpy(g["w0"]).double().clone()
+        return [float(o.step(fg, w)[0]) for _ in range(8)]
+    losses = [float(opt.step(closure)[0]) for _ in range(8)]
+    assert next(model.parameters()).dtype == torch.float64
+    d, br = branch_distance(losses, orun, 8, seeds=8, eps=1e-7)
+    assert d < 1e-4, (losses, br)
