@@ -227,7 +227,7 @@ int decide_t(double* state, double* ws, const void* loss, const void* trial_loss
         constexpr int K = decltype(kc)::value;
         DecideOp<HT, VT, WT, K, true> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT*)g_trial, (const VT*)g_old,
                                          (VT*)g_out, (const VT*)p, (WT*)w, (HT*)S, (HT*)Y, ld, loss_out, copy_old};
-        return launch_sel<FAST>(op, n, vec, ws, 2, TILE * (int)(3 * sizeof(VT) + 2 * K * sizeof(HT)), K <= 4, s);
+        return launch_sel<FAST>(op, n, vec, ws, 2, TILE * (int)(3 * sizeof(VT) + 2 * K * sizeof(HT)), K == 6, s);   // measured: TMA wins at K=6 only
     };
     DD4ML_RUN_K(FAST, kcap, run)
 }

@@ -73,7 +73,7 @@ int propose_t(double* state, double* ws, const void* g, const void* S, const voi
     auto run = [&](auto kc) {
         constexpr int K = decltype(kc)::value;
         ProposeOp<HT, VT, K> op{(dd4ml_state*)state, (const VT*)g, (const HT*)S, (const HT*)Y, ld, mode};
-        return launch_sel<FAST>(op, n, vec, ws, 3, TILE * (int)(sizeof(VT) + 2 * K * sizeof(HT)), false, s);
+        return launch_sel<FAST>(op, n, vec, ws, 3, TILE * (int)(sizeof(VT) + 2 * K * sizeof(HT)), K == 6, s);
     };
     DD4ML_RUN_K(FAST, kcap, run)
 }

@@ -298,4 +298,6 @@ class APTS_Base(Optimizer):
         pred_t = as_device_scalar(pred, self.device)
         out, g, delta, _, _ = self._control(step.contiguous(), 0, 1.0, 0.0, self.init_glob_loss,
                                             _lib.ptr(pred_t), _lib.dt(pred_t.dtype), None)
+        if delta is None:               # device-control mode: the public form reports delta to the host
+            delta, _, _ = self._read_control()
         return out, g, delta

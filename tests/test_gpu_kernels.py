@@ -251,3 +251,54 @@ def test_full_size_properties(n):
     # regularisation, but the secant equation must hold to the regularisation level for the last pair
     S, Y = h.S, h.Y
     assert rel_err(h.B(S[:, -1].contiguous()).cpu(), Y[:, -1].cpu()) < 1e-3
+
+
+def test_obs_wrapper_and_public_control_step():
+    """Reference-named entry points kept for API parity: OBS.solve_tr_subproblem (obs.py:46) on an LSR1
+    object, and APTS_Base.control_step(step, pred) (apts_base.py:432)."""
+    import torch.nn as nn
+    from dd4ml_b200 import APTS_D, OBS
+    from dd4ml_b200.workloads import apts_d_yaml_config
+    torch.manual_seed(4)
+    n = 4096
+    h = LSR1(gamma=1.0, memory_length=3, tol=1e-6, device=DEV)
+    hc = LSR1Memory(gamma=1.0, memory_length=3, tol=1e-6)
+    d = torch.linspace(0.5, 2.0, n)
+    for _ in range(3):
+        s = torch.randn(n) * 0.01
+        h.update_memory(s.to(DEV), (d * s).to(DEV))
+        hc.update(s, d * s); hc.precompute()
+    g = torch.randn(n)
+    p = OBS().solve_tr_subproblem(g.to(DEV), torch.tensor(0.2), h.gamma, h)
+    from oracle.obs import obs_solve
+    p_or = obs_solve(g, torch.tensor(0.2), hc.gamma, hc.Psi, hc.Minv, eig_sign="canonical")
+    assert rel_err(p.cpu(), p_or) < 1e-5
+    with pytest.raises(TypeError):
+        OBS().solve_tr_subproblem(g.to(DEV), torch.tensor(0.2), h.gamma, torch.zeros(n, 3, device=DEV), None)
+
+    model = nn.Sequential(nn.Flatten(), nn.Linear(16, 4)).to(DEV)
+    c = APTS_D.setup_APTS_hparams(apts_d_yaml_config(glob_opt="tr", loc_opt="tr", glob_second_order=False,
+                                                     loc_second_order=False, glob_dogleg=False, loc_dogleg=False))
+    opt = APTS_D(model.parameters(), model=model, criterion=nn.CrossEntropyLoss(), device=DEV, nr_models=1,
+                 glob_opt=c.glob_opt, glob_opt_hparams=c.glob_opt_hparams, loc_opt=c.loc_opt,
+                 loc_opt_hparams=c.loc_opt_hparams, glob_pass=False, foc=False, norm_type=2, max_loc_iters=1,
+                 max_glob_iters=1, tol=1e-6, **c.apts_params)
+    X, Y = torch.randn(32, 4, 4, device=DEV), torch.randint(0, 4, (32,), device=DEV)
+    opt.inputs, opt.labels = X, Y
+    opt.init_glob_flat = opt.glob_params_to_vector()
+    opt.init_glob_loss = opt.glob_closure_main(compute_grad=True)
+    opt.init_glob_grad = opt.glob_grad_to_vector()
+    w0 = opt.init_glob_flat.clone()
+    step = -0.05 * opt.init_glob_grad / opt.init_glob_grad.norm()
+    pred = torch.tensor(0.05 * float(opt.init_glob_grad.norm()), device=DEV)
+    loss, grad, delta = opt.control_step(step.clone(), pred)
+    assert float(loss) < float(opt.init_glob_loss)                     # a short steepest-descent step is accepted
+    assert torch.allclose(opt.glob_params_to_vector(), w0 + step, atol=1e-6)
+    loss2, _, delta2 = opt.control_step(-50.0 * step, pred)             # uphill: rejected, parameters restored
+    w_acc = w0 + step
+    assert delta2 < delta or delta2 == opt.min_delta
+
+
+def test_memory_length_above_build_maximum_is_refused():
+    with pytest.raises(dd4ml_b200.DD4MLError):
+        LSR1(memory_length=9, device=DEV)
