@@ -120,8 +120,7 @@ class APTS_Base(Optimizer):
         if self._bufs is None or self._bufs_version != ver:
             n, dev, wt = self._gfs.n, self.device, self._gfs.dtype
             z = lambda k=n, d=wt: torch.zeros(k, dtype=d, device=dev)  # noqa: E731
-            self._bufs = {"w0": z(), "g0": z(), "gl0": z(), "resid": z(), "comm": z(n + 2),
-                          "loss_out": torch.zeros((), dtype=torch.float32, device=dev)}
+            self._bufs = {"w0": z(), "g0": z(), "gl0": z(), "resid": z(), "comm": z(n + 2)}
             self._bufs_version = ver
         return self._bufs
 

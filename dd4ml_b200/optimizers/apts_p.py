@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from .. import _lib
-from ..flat import FlatBuffer, FlatSlice, get_flat
+from ..flat import FlatBuffer, FlatSlice
 from ..utility.apts_utils import clone_model, mark_trainable
 from .apts_base import APTS_Base
 from .tr import as_device_scalar

@@ -154,10 +154,6 @@ class TR(Optimizer):
             self._bufs[dtype] = b
         return b
 
-    def _grad_dtype(self):
-        # tr.py:69: the gradient buffer is fp32 unless the flat_grads_fn hook supplies it
-        return torch.float32
-
     def _current_grad(self, vt) -> torch.Tensor:
         """Flat view of the gradient the last backward produced, in dtype vt."""
         if self._flat_grads_fn is not None:

@@ -343,3 +343,21 @@ def test_tr_float64_parameters_fp32_gradient_buffer(so):
     assert next(model.parameters()).dtype == torch.float64
     d, br = branch_distance(losses, orun, 8, seeds=8, eps=1e-7)
     assert d < 1e-4, (losses, br)
+
+
+def test_lssr1_strict_read_order_matches_reference(monkeypatch):
+    """DD4ML_B200_DEVICE_CONTROL=0: the convergence test is read before the first line-search
+    evaluation (the reference's order of operations, lssr1_tr.py:509); default folds the two reads."""
+    monkeypatch.setenv("DD4ML_B200_DEVICE_CONTROL", "0")
+    g = load_golden("lssr1_fo")
+    X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
+    model = gpu_model(g)
+    hp = get_lssr1_tr_hparams(cfg(glob_second_order=False))
+    hp["sync"] = False
+    opt = LSSR1_TR(model.parameters(), **hp)
+    assert opt.speculative_first_eval is False
+    closure = make_closure(opt, model, X, Y)
+    s0 = opt._ds.syncs
+    losses = [float(opt.step(closure)[0]) for _ in range(10)]
+    np.testing.assert_allclose(losses, g["loss"][:10], rtol=2e-4)
+    assert opt._ds.syncs - s0 == 10 + opt.n_evals        # one read per step + one per evaluation

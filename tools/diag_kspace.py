@@ -1,5 +1,5 @@
 """Diagnostics (GPU): k-space cycle counters of the LSSR1 local/global steps of the bench workload."""
-import sys, os, json
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import build_optimizer, PER_RANK_BATCH

@@ -26,7 +26,6 @@ from dd4ml_b200.workloads import mnist_shape_batch
 model, opt = build_optimizer(dev, world)
 X, Y = mnist_shape_batch(PER_RANK_BATCH, 1234 + rank, device=dev)
 for _ in range(5): opt.step(X, Y)
-import dd4ml_b200.optimizers.apts_base as ab
 acc = {}
 def timed(name, fn):
     def w(*a, **k):
@@ -38,7 +37,6 @@ opt.glob_closure_main = timed("glob_closure", opt.glob_closure_main)
 opt.loc_steps = timed("loc_steps", opt.loc_steps)
 opt.glob_steps = timed("glob_steps", opt.glob_steps)
 opt._allreduce_mean = timed("allreduce_mean", opt._allreduce_mean)
-orig_ar = dist.all_reduce
 torch.cuda.synchronize(); dist.barrier()
 t0 = time.perf_counter()
 N = 20

@@ -3,7 +3,6 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import large_n_roofline
-import json
 peak = 6459.3
 n = int(os.environ.get("SWEEP_N", 1 << 26))
 k = int(os.environ.get("SWEEP_K", 3))
