@@ -24,7 +24,7 @@ struct PairRegs {
                                          int64_t ld, const Slots<KMAX>& sl, int64_t i) {
 #pragma unroll
         for (int j = 0; j < KMAX; ++j)
-            if (j < sl.k) {
+            if (sl.live(j)) {
                 l.template get<V, HT>(F + j, S + (int64_t)sl.slot[j] * ld, i, false, s[j]);
                 l.template get<V, HT>(F + KMAX + j, Y + (int64_t)sl.slot[j] * ld, i, false, y[j]);
             }
@@ -34,7 +34,7 @@ struct PairRegs {
                                                 const void*& p, int& esz) {
         const int j = r < KMAX ? r : r - KMAX;
         esz = (int)sizeof(HT);
-        p = (j < sl.k) ? (const void*)((r < KMAX ? S : Y) + (int64_t)sl.slot[j] * ld) : nullptr;
+        p = sl.live(j) ? (const void*)((r < KMAX ? S : Y) + (int64_t)sl.slot[j] * ld) : nullptr;
     }
 };
 

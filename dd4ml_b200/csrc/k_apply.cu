@@ -7,7 +7,7 @@ template <class HT, class VT, class WT, int KMAX>
 struct ApplyOp {
     static constexpr int NRED = 1;
     static constexpr bool SMEM_STATE = false;
-    static constexpr int F = 2, NS_MAX = F + 2 * KMAX;
+    static constexpr int F = 2, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4;
     __host__ __device__ static constexpr bool is_max(int) { return true; }
     dd4ml_state* st;
     const VT* g;
@@ -24,14 +24,17 @@ struct ApplyOp {
         sl.load(st, true);
         cg = st->cg[0];
         conv = st->converged[0] != 0.0;
-        int kk = 0;  // keep only slots with non-zero coefficients (first-order step: none)
+        unsigned m = 0;  // stream only slots with non-zero coefficients (first-order step: none)
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j)
+        for (int j = 0; j < KMAX; ++j) {
+            cS[j] = cY[j] = 0.0;
             if (j < sl.k) {
-                const double a = st->cS[sl.slot[j]], b = st->cY[sl.slot[j]];
-                if (a != 0.0 || b != 0.0) { cS[kk] = a; cY[kk] = b; sl.slot[kk] = sl.slot[j]; ++kk; }
+                cS[j] = st->cS[sl.slot[j]];
+                cY[j] = st->cY[sl.slot[j]];
+                if (cS[j] != 0.0 || cY[j] != 0.0) m |= 1u << j;
             }
-        sl.k = kk;
+        }
+        sl.mask = m;
     }
     __device__ bool active() const { return true; }
     __device__ bool use_tma() const { return !conv; }
@@ -61,7 +64,7 @@ struct ApplyOp {
         for (int e = 0; e < V; ++e) pv[e] = cg * (double)gr.x[e];
 #pragma unroll
         for (int j = 0; j < KMAX; ++j)
-            if (j < sl.k) {
+            if (sl.live(j)) {
 #pragma unroll
                 for (int e = 0; e < V; ++e) pv[e] += cS[j] * (double)pr.s[j].x[e] + cY[j] * (double)pr.y[j].x[e];
             }
@@ -92,7 +95,7 @@ int apply_t(double* state, double* ws, const void* g, const void* S, const void*
     auto run = [&](auto kc) {
         constexpr int K = decltype(kc)::value;
         ApplyOp<HT, VT, WT, K> op{(dd4ml_state*)state, (const VT*)g, (const HT*)S, (const HT*)Y, (VT*)p, (WT*)w, ld};
-        return launch_sel<FAST>(op, n, vec, ws, 3, TILE * (int)(sizeof(VT) + sizeof(WT) + 2 * K * sizeof(HT)), K <= 6, s);
+        return launch_sel<FAST>(op, n, vec, ws, 3, TILE * (int)(sizeof(VT) + sizeof(WT) + 2 * K * sizeof(HT)), true, s);
     };
     DD4ML_RUN_K(FAST, kcap, run)
 }

@@ -7,7 +7,7 @@ template <class HT, class VT, class WT, int KMAX>
 struct LssrBeginOp {
     static constexpr int NRED = 7 + 6 * KMAX;
     static constexpr bool SMEM_STATE = true;
-    static constexpr int F = 4, NS_MAX = F + 2 * KMAX;
+    static constexpr int F = 4, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
     const WT* w;
@@ -76,7 +76,7 @@ struct LssrBeginOp {
         }
 #pragma unroll
         for (int j = 0; j < KMAX; ++j)
-            if (j < sl.k) {
+            if (sl.live(j)) {
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
                     const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
@@ -101,7 +101,7 @@ struct LssrBeginOp {
         t->gg[0] = s[0];
         t->ginf[0] = s[1];
         t->loss[0] = ld_scalar(lossp, lt);
-        for (int j = 0; j < sl.k; ++j) { t->Sg[sl.slot[j]] = s[7 + j]; t->Yg[sl.slot[j]] = s[7 + KMAX + j]; }
+        for (int j = 0; j < sl.k; ++j) { t->Sg[sl.at(j)] = s[7 + j]; t->Yg[sl.at(j)] = s[7 + KMAX + j]; }
         t->pair_tried[0] = 0.0;
         t->pair_ok[0] = 0.0;
         t->err[0] = 0.0;
@@ -111,10 +111,10 @@ struct LssrBeginOp {
             t->c_ss[0] = s[2]; t->c_sy[0] = s[3]; t->c_yy[0] = s[4];
             t->c_sg[0] = s[5]; t->c_yg[0] = s[6];
             for (int j = 0; j < sl.k; ++j) {
-                t->c_Ss[sl.slot[j]] = s[7 + 2 * KMAX + j];
-                t->c_Ys[sl.slot[j]] = s[7 + 3 * KMAX + j];
-                t->c_Sy[sl.slot[j]] = s[7 + 4 * KMAX + j];
-                t->c_Yy[sl.slot[j]] = s[7 + 5 * KMAX + j];
+                t->c_Ss[sl.at(j)] = s[7 + 2 * KMAX + j];
+                t->c_Ys[sl.at(j)] = s[7 + 3 * KMAX + j];
+                t->c_Sy[sl.at(j)] = s[7 + 4 * KMAX + j];
+                t->c_Yy[sl.at(j)] = s[7 + 5 * KMAX + j];
             }
             const double tol = t->tol[0];
             if (sqrt(s[2]) > tol && sqrt(s[4]) > tol) {  // lssr1_tr.py:521
@@ -142,7 +142,7 @@ int begin_t(double* state, double* ws, const void* w, void* old_w, const void* g
         LssrBeginOp<HT, VT, WT, K> op{(dd4ml_state*)state, (const WT*)w, (WT*)old_w, (const VT*)g, (VT*)prev_g,
                                       (HT*)S, (HT*)Y, ld, has_prev, loss, lt};
         return launch_sel<FAST>(op, n, vec, ws, K <= 4 ? 2 : 1,
-                                TILE * (int)(2 * sizeof(WT) + 2 * sizeof(VT) + 2 * K * sizeof(HT)), K <= 4, s);
+                                TILE * (int)(2 * sizeof(WT) + 2 * sizeof(VT) + 2 * K * sizeof(HT)), true, s);
     };
     DD4ML_RUN_K(FAST, kcap, run)
 }

@@ -7,7 +7,7 @@ template <class HT, class VT, class WT, int KMAX, bool MEM>
 struct DecideOp {
     static constexpr int NRED = 5 + 4 * KMAX;
     static constexpr bool SMEM_STATE = true;
-    static constexpr int F = 3, NS_MAX = F + 2 * KMAX;
+    static constexpr int F = 3, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 4; }
     dd4ml_state* st;
     const void* loss;
@@ -35,8 +35,10 @@ struct DecideOp {
         f1 = ld_scalar(trial, lt);
         conv = st->converged[0] != 0.0;
         if (conv) { accept = false; rho = 0.0; return; }
-        accept = (lt == 0) ? ks::tr_accept<float>(f0, f1, st->pred[0], st->tol[0], st->nu_dec[0], &rho)
-                           : ks::tr_accept<double>(f0, f1, st->pred[0], st->tol[0], st->nu_dec[0], &rho);
+        double r = 0.0;   // (not &rho: the op must stay in registers)
+        accept = (lt == 0) ? ks::tr_accept<float>(f0, f1, st->pred[0], st->tol[0], st->nu_dec[0], &r)
+                           : ks::tr_accept<double>(f0, f1, st->pred[0], st->tol[0], st->nu_dec[0], &r);
+        rho = r;
     }
     __device__ bool active() const { return !conv || copy_old; }
     __device__ bool use_tma() const { return accept; }
@@ -95,7 +97,7 @@ struct DecideOp {
             }
 #pragma unroll
             for (int j = 0; j < KMAX; ++j)
-                if (j < sl.k) {
+                if (sl.live(j)) {
 #pragma unroll
                     for (int e = 0; e < V; ++e) {
                         const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
@@ -123,10 +125,10 @@ struct DecideOp {
             t->c_ss[0] = s[0]; t->c_sy[0] = s[1]; t->c_yy[0] = s[2];
             t->out_gg[0] = s[3]; t->out_ginf[0] = s[4];
             for (int j = 0; j < sl.k; ++j) {
-                t->c_Ss[sl.slot[j]] = s[5 + j];
-                t->c_Ys[sl.slot[j]] = s[5 + KMAX + j];
-                t->c_Sy[sl.slot[j]] = s[5 + 2 * KMAX + j];
-                t->c_Yy[sl.slot[j]] = s[5 + 3 * KMAX + j];
+                t->c_Ss[sl.at(j)] = s[5 + j];
+                t->c_Ys[sl.at(j)] = s[5 + KMAX + j];
+                t->c_Sy[sl.at(j)] = s[5 + 2 * KMAX + j];
+                t->c_Yy[sl.at(j)] = s[5 + 3 * KMAX + j];
             }
         }
         const double so = t->second_order[0];
@@ -142,7 +144,7 @@ template <class HT, class VT, int KMAX>
 struct UpdateOp {
     static constexpr int NRED = 3 + 4 * KMAX;
     static constexpr bool SMEM_STATE = true;
-    static constexpr int F = 2, NS_MAX = F + 2 * KMAX;
+    static constexpr int F = 2, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     dd4ml_state* st;
     const VT* s_in;
@@ -182,7 +184,7 @@ struct UpdateOp {
         }
 #pragma unroll
         for (int j = 0; j < KMAX; ++j)
-            if (j < sl.k) {
+            if (sl.live(j)) {
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
                     const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
@@ -198,10 +200,10 @@ struct UpdateOp {
     __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
         t->c_ss[0] = s[0]; t->c_sy[0] = s[1]; t->c_yy[0] = s[2];
         for (int j = 0; j < sl.k; ++j) {
-            t->c_Ss[sl.slot[j]] = s[3 + j];
-            t->c_Ys[sl.slot[j]] = s[3 + KMAX + j];
-            t->c_Sy[sl.slot[j]] = s[3 + 2 * KMAX + j];
-            t->c_Yy[sl.slot[j]] = s[3 + 3 * KMAX + j];
+            t->c_Ss[sl.at(j)] = s[3 + j];
+            t->c_Ys[sl.at(j)] = s[3 + KMAX + j];
+            t->c_Sy[sl.at(j)] = s[3 + 2 * KMAX + j];
+            t->c_Yy[sl.at(j)] = s[3 + 3 * KMAX + j];
         }
         t->err[0] = 0.0;
         t->pair_tried[0] = 1.0;
@@ -227,7 +229,7 @@ int decide_t(double* state, double* ws, const void* loss, const void* trial_loss
         constexpr int K = decltype(kc)::value;
         DecideOp<HT, VT, WT, K, true> op{(dd4ml_state*)state, loss, trial_loss, lt, (const VT*)g_trial, (const VT*)g_old,
                                          (VT*)g_out, (const VT*)p, (WT*)w, (HT*)S, (HT*)Y, ld, loss_out, copy_old};
-        return launch_sel<FAST>(op, n, vec, ws, 2, TILE * (int)(3 * sizeof(VT) + 2 * K * sizeof(HT)), K == 6, s);   // measured: TMA wins at K=6 only
+        return launch_sel<FAST>(op, n, vec, ws, 2, TILE * (int)(3 * sizeof(VT) + 2 * K * sizeof(HT)), true, s);
     };
     DD4ML_RUN_K(FAST, kcap, run)
 }
@@ -239,7 +241,7 @@ int update_t(double* state, double* ws, const void* s_in, const void* y_in, void
     auto run = [&](auto kc) {
         constexpr int K = decltype(kc)::value;
         UpdateOp<HT, VT, K> op{(dd4ml_state*)state, (const VT*)s_in, (const VT*)y_in, (HT*)S, (HT*)Y, ld};
-        return launch_sel<FAST>(op, n, vec, ws, 2, TILE * (int)(2 * sizeof(VT) + 2 * K * sizeof(HT)), K <= 4, s);
+        return launch_sel<FAST>(op, n, vec, ws, 2, TILE * (int)(2 * sizeof(VT) + 2 * K * sizeof(HT)), true, s);
     };
     DD4ML_RUN_K(FAST, kcap, run)
 }

@@ -7,7 +7,7 @@ template <class HT, class VT, int KMAX>
 struct ProposeOp {
     static constexpr int NRED = 2 + 2 * KMAX;
     static constexpr bool SMEM_STATE = true;
-    static constexpr int F = 1, NS_MAX = F + 2 * KMAX;
+    static constexpr int F = 1, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
     const VT* g;
@@ -41,7 +41,7 @@ struct ProposeOp {
         }
 #pragma unroll
         for (int j = 0; j < KMAX; ++j)
-            if (j < sl.k) {
+            if (sl.live(j)) {
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
                     acc[2 + j] += (double)pr.s[j].x[e] * gv[e];
@@ -52,7 +52,7 @@ struct ProposeOp {
     __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
         t->gg[0] = s[0];
         t->ginf[0] = s[1];
-        for (int j = 0; j < sl.k; ++j) { t->Sg[sl.slot[j]] = s[2 + j]; t->Yg[sl.slot[j]] = s[2 + KMAX + j]; }
+        for (int j = 0; j < sl.k; ++j) { t->Sg[sl.at(j)] = s[2 + j]; t->Yg[sl.at(j)] = s[2 + KMAX + j]; }
         if (mode == 2) ks::lsr1_B_coefs(t, scr);
         else if (sl.k > 0) ks::tr_solve<HT>(t, mode, scr);   // OBS works in the dtype of Psi (obs.py:88)
         else ks::tr_solve<VT>(t, mode, scr);
@@ -73,7 +73,7 @@ int propose_t(double* state, double* ws, const void* g, const void* S, const voi
     auto run = [&](auto kc) {
         constexpr int K = decltype(kc)::value;
         ProposeOp<HT, VT, K> op{(dd4ml_state*)state, (const VT*)g, (const HT*)S, (const HT*)Y, ld, mode};
-        return launch_sel<FAST>(op, n, vec, ws, 3, TILE * (int)(sizeof(VT) + 2 * K * sizeof(HT)), K == 6, s);
+        return launch_sel<FAST>(op, n, vec, ws, 3, TILE * (int)(sizeof(VT) + 2 * K * sizeof(HT)), true, s);   // measured: TMA wins for every K
     };
     DD4ML_RUN_K(FAST, kcap, run)
 }

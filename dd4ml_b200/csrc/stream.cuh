@@ -63,8 +63,37 @@ __device__ __forceinline__ void ld_rw<1, float>(const float* p, int64_t i, doubl
 template <>
 __device__ __forceinline__ void ld_rw<1, double>(const double* p, int64_t i, double (&v)[1]) { v[0] = p[i]; }
 
+template <>
+__device__ __forceinline__ void ld_ro<2, float>(const float* __restrict__ p, int64_t i, double (&v)[2]) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p + i));
+    v[0] = t.x; v[1] = t.y;
+}
+template <>
+__device__ __forceinline__ void ld_ro<2, double>(const double* __restrict__ p, int64_t i, double (&v)[2]) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p + i));
+    v[0] = a.x; v[1] = a.y;
+}
+template <>
+__device__ __forceinline__ void ld_rw<2, float>(const float* p, int64_t i, double (&v)[2]) {
+    const float2 t = *reinterpret_cast<const float2*>(p + i);
+    v[0] = t.x; v[1] = t.y;
+}
+template <>
+__device__ __forceinline__ void ld_rw<2, double>(const double* p, int64_t i, double (&v)[2]) {
+    const double2 a = *reinterpret_cast<const double2*>(p + i);
+    v[0] = a.x; v[1] = a.y;
+}
+
 template <int V, class T>
 __device__ __forceinline__ void st_v(T* p, int64_t i, const double (&v)[V]);
+template <>
+__device__ __forceinline__ void st_v<2, float>(float* p, int64_t i, const double (&v)[2]) {
+    *reinterpret_cast<float2*>(p + i) = make_float2((float)v[0], (float)v[1]);
+}
+template <>
+__device__ __forceinline__ void st_v<2, double>(double* p, int64_t i, const double (&v)[2]) {
+    *reinterpret_cast<double2*>(p + i) = make_double2(v[0], v[1]);
+}
 template <>
 __device__ __forceinline__ void st_v<4, float>(float* p, int64_t i, const double (&v)[4]) {
     *reinterpret_cast<float4*>(p + i) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
@@ -93,6 +122,14 @@ template <> __device__ __forceinline__ void ldr_ro<4, double>(Raw<4, double>& r,
     const double2 b = __ldg(reinterpret_cast<const double2*>(p + i + 2));
     r.x[0] = a.x; r.x[1] = a.y; r.x[2] = b.x; r.x[3] = b.y;
 }
+template <> __device__ __forceinline__ void ldr_ro<2, float>(Raw<2, float>& r, const float* __restrict__ p, int64_t i) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p + i));
+    r.x[0] = t.x; r.x[1] = t.y;
+}
+template <> __device__ __forceinline__ void ldr_ro<2, double>(Raw<2, double>& r, const double* __restrict__ p, int64_t i) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p + i));
+    r.x[0] = a.x; r.x[1] = a.y;
+}
 template <> __device__ __forceinline__ void ldr_ro<1, float>(Raw<1, float>& r, const float* __restrict__ p, int64_t i) { r.x[0] = __ldg(p + i); }
 template <> __device__ __forceinline__ void ldr_ro<1, double>(Raw<1, double>& r, const double* __restrict__ p, int64_t i) { r.x[0] = __ldg(p + i); }
 template <int V, class T> __device__ __forceinline__ void ldr_rw(Raw<V, T>& r, const T* p, int64_t i);
@@ -104,6 +141,14 @@ template <> __device__ __forceinline__ void ldr_rw<4, double>(Raw<4, double>& r,
     const double2 a = *reinterpret_cast<const double2*>(p + i);
     const double2 b = *reinterpret_cast<const double2*>(p + i + 2);
     r.x[0] = a.x; r.x[1] = a.y; r.x[2] = b.x; r.x[3] = b.y;
+}
+template <> __device__ __forceinline__ void ldr_rw<2, float>(Raw<2, float>& r, const float* p, int64_t i) {
+    const float2 t = *reinterpret_cast<const float2*>(p + i);
+    r.x[0] = t.x; r.x[1] = t.y;
+}
+template <> __device__ __forceinline__ void ldr_rw<2, double>(Raw<2, double>& r, const double* p, int64_t i) {
+    const double2 a = *reinterpret_cast<const double2*>(p + i);
+    r.x[0] = a.x; r.x[1] = a.y;
 }
 template <> __device__ __forceinline__ void ldr_rw<1, float>(Raw<1, float>& r, const float* p, int64_t i) { r.x[0] = p[i]; }
 template <> __device__ __forceinline__ void ldr_rw<1, double>(Raw<1, double>& r, const double* p, int64_t i) { r.x[0] = p[i]; }
@@ -119,15 +164,26 @@ __device__ __forceinline__ void st_scalar(void* p, int dt, double v) {
 }
 
 // live slots of the L-SR1 ring, read once per thread from the state block
+// Only ever indexed with compile-time constants (unrolled loops, at()): a dynamic index would
+// push the whole op into local memory and turn every field access of the hot loop into an LDL.
 template <int KMAX>
 struct Slots {
     int k;
+    unsigned mask;   // bit j set: pair j is streamed
     int slot[KMAX > 0 ? KMAX : 1];
     __device__ __forceinline__ void load(const dd4ml_state* st, bool use_memory) {
         k = use_memory ? (int)st->k[0] : 0;
         if (k > KMAX) k = KMAX;
+        mask = (1u << k) - 1u;
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) slot[j] = (j < k) ? (int)st->order[j] : 0;
+    }
+    __device__ __forceinline__ bool live(int j) const { return (mask >> j) & 1u; }
+    __device__ __forceinline__ int at(int j) const {   // runtime j (finalize only)
+        int r = slot[0];
+#pragma unroll
+        for (int i = 1; i < KMAX; ++i) r = (j == i) ? slot[i] : r;
+        return r;
     }
 };
 
@@ -172,14 +228,20 @@ __device__ __forceinline__ void finish_reduce(Op& op, double* acc, double* ws) {
         __syncthreads();
         if (s_last) {
             __threadfence();
-            if (threadIdx.x < NR) {
-                const int j = threadIdx.x;
+            // one warp per column: lanes stride over the CTAs' partials, then a butterfly -- a fixed
+            // tree for a given grid (bit-reproducible), and ~G/32 dependent L2 reads instead of G
+            for (int j = warp; j < NR; j += NW) {
                 double v = 0.0;
-                for (unsigned int b = 0; b < gridDim.x; ++b) {
+                for (unsigned int b = lane; b < gridDim.x; b += 32) {
                     const double u = __ldcg(partials + (int64_t)b * NR + j);
                     v = Op::is_max(j) ? fmax(v, u) : v + u;
                 }
-                s_sum[j] = v;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double u = __shfl_xor_sync(0xffffffffu, v, o);
+                    v = Op::is_max(j) ? fmax(v, u) : v + u;
+                }
+                if (lane == 0) s_sum[j] = v;
             }
             __syncthreads();
             if constexpr (Op::SMEM_STATE) {
