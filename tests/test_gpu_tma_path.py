@@ -1,6 +1,6 @@
 """Re-run the kernel and optimizer parity tests with every vector routed through the
 TMA-staged kernels (DD4ML_B200_TMA_MIN_N=0, DD4ML_B200_TMA_MODE=1; by default only the
-update/decide/begin ops at n >= 2^20 take that path)."""
+heavy ops at n >= 2^20 take that path)."""
 import os
 import subprocess
 import sys
@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def test_parity_suite_through_tma_kernels():
     env = dict(os.environ, DD4ML_B200_TMA_MIN_N="0", DD4ML_B200_TMA_MODE="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_kernels.py"),
-                        os.path.join(HERE, "test_gpu_optimizers.py"), "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"],
+                        os.path.join(HERE, "test_gpu_optimizers.py"), os.path.join(HERE, "test_gpu_configs.py"), "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
 
