@@ -12,6 +12,7 @@ from .optimizers.apts_pinn import APTS_PINN  # noqa: F401
 from .optimizers.lsr1 import LSR1  # noqa: F401
 from .optimizers.lssr1_tr import LSSR1_TR  # noqa: F401
 from .optimizers.tr import TR  # noqa: F401
+from .optimizers.tradam import TRAdam  # noqa: F401
 from .solvers.obs import OBS  # noqa: F401
 from .install import install  # noqa: F401
 

@@ -16,6 +16,7 @@ _MODULES = {
     "dd4ml.optimizers.tr": "dd4ml_b200.optimizers.tr",
     "dd4ml.optimizers.lsr1": "dd4ml_b200.optimizers.lsr1",
     "dd4ml.optimizers.lssr1_tr": "dd4ml_b200.optimizers.lssr1_tr",
+    "dd4ml.optimizers.tradam": "dd4ml_b200.optimizers.tradam",
     "dd4ml.optimizers.apts_base": "dd4ml_b200.optimizers.apts_base",
     "dd4ml.optimizers.apts_d": "dd4ml_b200.optimizers.apts_d",
     "dd4ml.optimizers.apts_p": "dd4ml_b200.optimizers.apts_p",

@@ -97,6 +97,37 @@ class APTS_Base(Optimizer):
         self._glob_eval = None if self._is_ddp else GraphedEval(self.model, self.criterion, self._gfs)
         self._loc_eval = None          # created by the subclass once the local model exists
         self._device_control = False   # see _enable_device_control
+        self._resync = False           # set by load_state_dict
+
+    # ------------------------------------------------------------------ checkpointing
+    def state_dict(self):
+        """Radius, evaluation counters and the inner optimizers' state (radius, L-SR1 memory).  The
+        local model is re-synchronised from the global one at the start of every outer iteration,
+        so it is not part of the state."""
+        sd = super().state_dict()
+        sd["dd4ml_b200"] = {"delta": float(self.delta), "grad_evals": float(self.grad_evals),
+                            "loc_grad_evals": float(self.loc_grad_evals),
+                            "glob": self.glob_opt.state_dict(),
+                            "loc": None if self.loc_opt is None else self.loc_opt.state_dict()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        extra = state_dict.pop("dd4ml_b200", None)
+        super().load_state_dict(state_dict)
+        if extra is None:
+            return
+        self.glob_opt.load_state_dict(extra["glob"])
+        if extra["loc"] is not None and self.loc_opt is not None:
+            self.loc_opt.load_state_dict(extra["loc"])
+        self.delta = float(extra["delta"])
+        self.grad_evals = float(extra["grad_evals"])
+        self.loc_grad_evals = float(extra["loc_grad_evals"])
+        self._ctl_pushed = {}
+        # the local clone mirrors the global model between outer iterations (sync_glob_to_loc at the
+        # end of step()); the caller may restore the model before or after this call, so the next
+        # step() re-establishes the invariant first
+        self._resync = True
 
     def _enable_device_control(self):
         """TR/TR configurations run an outer iteration with ONE host read at its end: the inner TR

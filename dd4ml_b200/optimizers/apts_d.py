@@ -109,6 +109,9 @@ class APTS_D(APTS_Base):
         (inputs, labels) pairs of the global and the local closure."""
         lib = self._ctl.lib
         self.grad_evals, self.loc_grad_evals = 0.0, 0.0
+        if self._resync:                 # first step after load_state_dict
+            self.sync_glob_to_loc()
+            self._resync = False
         if self._gfs.ensure() | self._lfs.ensure():
             pass
         b = self._buffers()

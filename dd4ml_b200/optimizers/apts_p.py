@@ -137,6 +137,9 @@ class APTS_P(APTS_Base):
         self.inputs, self.labels = inputs, labels
         self.inputs_d, self.labels_d, self.hNk = inputs_d, labels_d, hNk
         self.grad_evals, self.loc_grad_evals = 0.0, 0.0
+        if self._resync:                 # first step after load_state_dict
+            self.sync_glob_to_loc()
+            self._resync = False
         if self._gfs.ensure() or self._lfb.ensure():
             raise _lib.DD4MLError("dd4ml_b200 APTS_P: parameter storage changed after construction "
                                   "(convert the model dtype before building the optimizer)")

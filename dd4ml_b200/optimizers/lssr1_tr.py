@@ -331,3 +331,22 @@ class LSSR1_TR(Optimizer):
                             "old_w": None if self._bufs is None else self._bufs["old_w"].clone(),
                             "prev_g": None if self._bufs is None else self._bufs["prev_g"].clone()}
         return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        extra = state_dict.pop("dd4ml_b200", None)
+        super().load_state_dict(state_dict)
+        if extra is None:
+            return
+        self.hess.load_state_dict(extra["hess"])
+        self.gamma = self.hess.gamma
+        self.delta = float(extra["delta"])
+        self._pushed_delta = None
+        self._pre = None
+        self._has_prev = bool(extra["has_prev"]) and extra["old_w"] is not None
+        if extra["old_w"] is not None:
+            b = self._buffers(extra["prev_g"].dtype)
+            has_prev = self._has_prev          # _buffers() drops the history when it (re)allocates
+            b["old_w"].copy_(extra["old_w"])
+            b["prev_g"].copy_(extra["prev_g"])
+            self._has_prev = has_prev

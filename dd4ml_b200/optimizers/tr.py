@@ -301,7 +301,27 @@ class TR(Optimizer):
         return rep
 
     # ------------------------------------------------------------------ checkpointing
+    # The reference never persists TR state; a resumed run here continues bit-identically.
     def state_dict(self):
         sd = super().state_dict()
-        sd["dd4ml_b200"] = {"delta": self.delta, "hess": None if self.hess is None else self.hess.state_dict()}
+        sd["dd4ml_b200"] = {"delta": self.delta, "state": self._ds.state.clone(),
+                            "hess": None if self.hess is None else self.hess.state_dict()}
         return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        extra = state_dict.pop("dd4ml_b200", None)
+        super().load_state_dict(state_dict)
+        if extra is None:
+            return
+        if (extra["hess"] is None) != (self.hess is None):
+            raise ValueError("checkpoint and optimizer disagree on second_order")
+        if self.hess is not None:
+            self.hess.load_state_dict(extra["hess"])      # shares the state block with this optimizer
+        else:
+            self._ds.state.copy_(extra["state"])
+        self.delta = float(extra["delta"])
+        self._pushed = {}            # hyper-parameters of THIS instance are pushed again on the next step
+        self._ds.set(delta=self.delta)
+        self._known_gn = None
+        self._step_norm_cache = None

@@ -115,6 +115,19 @@ int dd4ml_apts_control(double* state, double* ws, const void* f0, const void* ft
                        const void* pred, int pt, void* w, const void* w0, void* g0, const void* G,
                        void* loss_out, const void* aux, int64_t n, int vt, int wt, void* stream);
 
+/* ---- TRAdam (optimizers/tradam.py:80-111): Adam direction clipped to the radius `lr` ---------
+ * moments: m <- b1 m + (1-b1) g, v <- b2 v + (1-b2) g^2 in place; s = (m/bc1)/(sqrt(v/bc2)+eps)
+ *          is reduced to its length (max|s| if norm_inf, else s.s -- not its root, tradam.py:101);
+ *          state.pnorm <- length, state.aux <- scale = lr/length if length > lr else lr.
+ *          bc1 = 1-b1^t, bc2 = 1-b2^t.  m, v, g of dtype vt.
+ * apply:   step = scale * s (recomputed from m, v), w <- w - step; `step` (nullable, dtype vt)
+ *          receives the applied step (the reference's _step_buf). */
+int dd4ml_tradam_moments(double* state, double* ws, const void* g, void* m, void* v, double beta1,
+                         double beta2, double bc1, double bc2, double eps, double lr, int norm_inf,
+                         int64_t n, int vt, void* stream);
+int dd4ml_tradam_apply(double* state, double* ws, const void* m, const void* v, void* w, void* step,
+                       double bc1, double bc2, double eps, int64_t n, int vt, int wt, void* stream);
+
 /* ---- flat-buffer plumbing (utility/apts_utils.py:17-62, tr.py:88-104) ---------------------
  * gather:   dst[off_i : off_i+len_i] = src_i  for up to 96 tensors per call (multi-tensor).
  * seg_copy: dst[dst_off_i : +len_i] = src[src_off_i : +len_i]; optional zero fill of dst

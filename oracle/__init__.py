@@ -32,3 +32,4 @@ from .subproblem import solve_first_order, solve_second_order  # noqa: F401
 from .tr import TROracle  # noqa: F401
 from .lssr1_tr import LSSR1TROracle  # noqa: F401
 from .apts import APTSDOracle, APTSPOracle, apts_hparams, tr_hparams, loc_tr_hparams, lssr1_hparams, lssr1_loc_hparams  # noqa: F401
+from .tradam import TRAdamOracle  # noqa: F401

@@ -7,7 +7,7 @@ Run in the authoring container only (needs /root/reference):
 
 The reference cannot travel to the GPU box, so the outputs (tests/golden/*.npz)
 are committed.  Everything here drives the reference's own classes
-(`dd4ml.optimizers.{tr,lssr1_tr,apts_d,apts_p,apts_pinn}`) through their public
+(`dd4ml.optimizers.{tr,lssr1_tr,apts_d,apts_p,apts_pinn,tradam}`) through their public
 API on synthetic tensors with fixed seeds; nothing is re-implemented.
 Recorded: torch version, thread count, seeds, per-step scalars, and for the first
 few sub-problem solves the full input/output vectors.
@@ -364,7 +364,41 @@ def run_kernel_level(name):
     save(name, out)
 
 
+def run_tradam(name, norm_type, lr, steps, dtype=torch.float32):
+    """TRAdam (optimizers/tradam.py) as a standalone optimizer; the closure back-propagates."""
+    from dd4ml.optimizers.tradam import TRAdam
+    model = make_model(dtype)
+    X, Y = make_data(256, dtype=dtype)
+    crit = nn.CrossEntropyLoss()
+    opt = TRAdam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8, norm_type=norm_type)
+
+    def closure():
+        opt.zero_grad()
+        loss = crit(model(X), Y)
+        loss.backward()
+        return loss
+
+    out = {"w0": flat(model).numpy(), "X": X.numpy(), "Y": Y.numpy()}
+    losses, ws, smax = [], [], []
+    for _ in range(steps):
+        losses.append(float(opt.step(closure)))
+        ws.append(flat(model).numpy())
+        smax.append(float(opt._step_buf.abs().max()))
+    out["loss"] = np.asarray(losses)
+    out["step_max"] = np.asarray(smax)
+    out["w_step1"], out["w_step5"], out["w_final"] = ws[0], ws[4], ws[-1]
+    out["m_final"], out["v_final"] = opt._m_buf.numpy().copy(), opt._v_buf.numpy().copy()
+    out["step_final"] = opt._step_buf.numpy().copy()
+    meta(out, steps=steps, lr=lr)
+    save(name, out)
+
+
 def main():
+    if "--only-tradam" in sys.argv:
+        torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+        run_tradam("tradam_inf", math.inf, 0.01, 20)
+        run_tradam("tradam_l2", 2, 0.5, 20)
+        return
     torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
     run_kernel_level("kernel_level")
     run_plain("tr_fo", lambda m: TR(m.parameters(), **tr_kwargs(False, False)), 30)
@@ -391,6 +425,8 @@ def main():
              dtype=torch.float64, port=29607)
     run_apts("apts_p_tr_so_ws2", "apts_p", 2, "tr", "tr", True, False, 3, 12, port=29608)
     run_pinn("apts_pinn_ws2", 2, 10, port=29609)
+    run_tradam("tradam_inf", math.inf, 0.01, 20)
+    run_tradam("tradam_l2", 2, 0.5, 20)
 
 
 if __name__ == "__main__":

@@ -361,3 +361,46 @@ def test_lssr1_strict_read_order_matches_reference(monkeypatch):
     losses = [float(opt.step(closure)[0]) for _ in range(10)]
     np.testing.assert_allclose(losses, g["loss"][:10], rtol=2e-4)
     assert opt._ds.syncs - s0 == 10 + opt.n_evals        # one read per step + one per evaluation
+
+
+# ------------------------------------------------------------------------------ checkpoint / resume
+@pytest.mark.parametrize("kind", ["tr_fo", "tr_so", "lssr1_so", "apts_d_tr", "apts_d_lssr1"])
+def test_state_dict_resume_is_bit_identical(kind):
+    """the reference never persists TR state; here a run restored from
+    state_dict() (radius, L-SR1 ring + Gram blocks, previous iterate/gradient) continues exactly."""
+    g = load_golden("apts_d_tr_fo_ws1")
+    X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
+
+    def build():
+        model = gpu_model(g)
+        if kind.startswith("apts"):
+            so = kind.endswith("lssr1")
+            name = "lssr1_tr" if so else "tr"
+            opt = _apts("d", model, name, name, cfg(glob_second_order=so, glob_dogleg=so, loc_second_order=so,
+                                                  loc_dogleg=so), foc=True)
+            return model, opt, lambda: float(opt.step(X, Y))
+        if kind.startswith("tr"):
+            opt = TR(model.parameters(), **get_tr_hparams(cfg(delta=0.1, min_delta=1e-3, max_delta=2.0,
+                                                              glob_second_order=kind == "tr_so")))
+        else:
+            hp = get_lssr1_tr_hparams(cfg(glob_second_order=True, glob_dogleg=True))
+            hp["sync"] = False
+            opt = LSSR1_TR(model.parameters(), **hp)
+        closure = make_closure(opt, model, X, Y)
+        return model, opt, lambda: float(opt.step(closure)[0].detach())
+
+    model, opt, step = build()
+    for _ in range(4):
+        step()
+    ckpt_model = {k: v.clone() for k, v in model.state_dict().items()}
+    ckpt_opt = opt.state_dict()
+    cont = [step() for _ in range(4)]
+    w_cont, d_cont = flat_of(model), float(opt.delta)
+
+    model2, opt2, step2 = build()
+    model2.load_state_dict(ckpt_model)
+    opt2.load_state_dict(ckpt_opt)
+    resumed = [step2() for _ in range(4)]
+    assert resumed == cont
+    assert torch.equal(flat_of(model2), w_cont)
+    assert float(opt2.delta) == d_cont

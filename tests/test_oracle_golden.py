@@ -212,3 +212,23 @@ def test_apts_pinn_trajectory_matches_reference():
     np.testing.assert_allclose(losses, g["loss"], rtol=5e-5)
     np.testing.assert_allclose(deltas, g["delta"], rtol=1e-12)
     assert rel_err(opt.w, g["w_final"]) < 1e-3
+
+
+# --------------------------------------------------------------- TRAdam
+@pytest.mark.parametrize("name,norm,lr", [("tradam_inf", math.inf, 0.01), ("tradam_l2", 2, 0.5)])
+def test_tradam_trajectory_matches_reference(name, norm, lr):
+    g = load_golden(name)
+    X, Y = _data(g)
+    fg = make_fg(FFNN(IN_F, HID, OUT), X, Y)
+    w = torch.from_numpy(g["w0"]).clone()
+    opt = oracle.TRAdamOracle(w.numel(), lr=lr, norm_type=norm)
+    losses = []
+    for i in range(int(g["steps"])):
+        losses.append(float(opt.step(fg, w)))
+        if i == 0:
+            assert rel_err(w, g["w_step1"]) < 1e-7
+    np.testing.assert_allclose(losses, g["loss"], rtol=TRAJ_RTOL)
+    assert rel_err(w, g["w_final"]) < VEC_RTOL
+    assert rel_err(opt.m, g["m_final"]) < VEC_RTOL
+    assert rel_err(opt.v, g["v_final"]) < VEC_RTOL
+    assert rel_err(opt.step_buf, g["step_final"]) < VEC_RTOL
