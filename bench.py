@@ -320,9 +320,10 @@ def main():
     X, Y = Xh.to(device), Yh.to(device)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
 
-    losses = []
+    losses, evals = [], []
     def step_resident(i):
         losses.append(opt.step(X, Y))
+        evals.append(float(opt.grad_evals))      # reference counter: global + mean local gradient evaluations
 
     for i in range(args.warmup):
         step_resident(i)
@@ -332,7 +333,9 @@ def main():
     def sync_count():
         return opt._ctl.syncs + opt.glob_opt._ds.syncs + opt.loc_opt._ds.syncs
     l0, s0 = lib.launches, sync_count()
+    del evals[:]
     ms, wall = timed_region(step_resident, args.steps, world, device, flush)
+    evals_per_step = sum(evals) / max(len(evals), 1)
     launches = lib.launches - l0
     host_syncs = (sync_count() - s0) / args.steps
     clocks = sampler.stop() if rank == 0 else None
@@ -405,6 +408,9 @@ def main():
         "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "outer_iters_per_sec": args.steps / (ms / 1e3), "wall_ms_per_step": wall * 1e3 / args.steps,
         "e2e": e2e, "gpu_launches": launches, "host_syncs_per_step": host_syncs,
+        # work per outer iteration is trajectory dependent (line-search evaluations): more subdomains
+        # take more evaluations per iteration, which the per-N ms_per_step reflects
+        "grad_evals_per_step": evals_per_step,
         "clocks": clocks, "roofline": roofline,
         "roofline_native": {"n": n, "k": kmem, "dominant": dominant, "own_kernel_ms_per_step": own_ms,
                             "own_kernel_share_of_step": own_ms / (ms / args.steps), "kernels": native,
