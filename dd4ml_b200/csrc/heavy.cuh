@@ -39,6 +39,6 @@ struct PairRegs {
 };
 
 #define DD4ML_KCAP_SWITCH(kcap, CALLK) \
-    if ((kcap) <= 4) { CALLK(4) } else if ((kcap) <= 6) { CALLK(6) } else { CALLK(8) }
+    if ((kcap) <= 4) { CALLK(4) } else if ((kcap) <= 6) { CALLK(6) } else { CALLK(DD4ML_MAXM) }
 
 }  // namespace

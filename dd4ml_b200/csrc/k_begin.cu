@@ -7,7 +7,9 @@ template <class HT, class VT, class WT, int KMAX>
 struct LssrBeginOp {
     static constexpr int NRED = 7 + 6 * KMAX;
     static constexpr bool SMEM_STATE = true;
-    static constexpr int F = 4, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4;
+    // KMAX = 10: 24 streams x 4 KB leave two stages in the ring; half tiles (4 stages) measured 0.50 -> 0.59
+    // of peak here, but lose on the ops with fewer streams (twice the loop overhead per element)
+    static constexpr int F = 4, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = KMAX > 6 ? 2 : 4;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
     const WT* w;

@@ -10,7 +10,7 @@
 // S^T S, S^T Y, Y^T Y indexed by PHYSICAL slot.
 #pragma once
 
-#define DD4ML_MAXM 8                    // largest supported memory length
+#define DD4ML_MAXM 10                   // largest supported memory length
 #define DD4ML_MAXS (DD4ML_MAXM + 1)     // physical slots = live pairs + 1 spare (candidate)
 #define DD4ML_G (DD4ML_MAXS * DD4ML_MAXS)
 

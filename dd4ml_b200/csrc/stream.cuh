@@ -21,7 +21,7 @@ constexpr int BLOCK = 256;
 constexpr int NWARP = BLOCK / 32;
 constexpr int NUM_SMS = 148;
 constexpr int MAXGRID = NUM_SMS * 4;
-constexpr int MAXRED = 64;
+constexpr int MAXRED = 72;
 constexpr int WS_PARTIALS = MAXGRID * MAXRED;
 constexpr int WS_DOUBLES = WS_PARTIALS + 8;  // + ticket counter
 

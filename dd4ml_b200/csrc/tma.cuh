@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int TILE = BLOCK * 4;          // elements per stream per stage
+constexpr int TILE = BLOCK * 4;          // elements per stream per stage (ops with TMA_V = 4)
 constexpr int MAX_STAGES = 6;
 constexpr int SMEM_BUDGET = 200 * 1024;  // dynamic shared memory for the ring (+ ~14 KB static)
 
@@ -53,7 +53,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // data from the shared-memory ring (same interface as GlobalLoader, heavy.cuh).  Every stream
 // of the TMA path has 4-byte elements (all-fp32 instantiations only), so stream `sid` sits at the
 // compile-time offset sid * TILE * 4 of its stage: one base register + immediates, no lookups.
-constexpr int STREAM_BYTES = TILE * 4;
+template <int STREAM_BYTES>
 struct SmemLoader {
     const unsigned char* mine;   // stage base + 4 V * threadIdx.x
     template <int V, class T>
@@ -87,9 +87,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // PW = 1: one producer warp (9 warps: ptxas may use 168 registers).  PW = 4: a whole producer
 // warpgroup that hands its registers to the two consumer warpgroups (setmaxnreg 40 / 232) and
 // exits after its loop -- for the ops whose accumulators do not fit 168 registers.
-template <class Op>
+template <class Op, int TILE>
 __device__ __forceinline__ void tma_produce(unsigned char* ring, uint64_t* full, uint64_t* empty,
                                             const void* const* s_ptr, uint32_t nlive, int64_t nv4, int nstage) {
+    constexpr int STREAM_BYTES = TILE * 4;
     constexpr int STAGE_BYTES = Op::NS_MAX * STREAM_BYTES;
     const int64_t ntiles = (nv4 + TILE - 1) / TILE;
     int stg = 0;
@@ -112,7 +113,9 @@ template <class Op, int CW, int PW>
 __global__ void __launch_bounds__((CW + PW) * 32, 1) tma_kernel(Op op, int64_t n, double* ws, int nstage) {
     static_assert(PW == 1 || (PW == 4 && CW == 8), "register hand-over needs whole warpgroups");
     constexpr int CT = CW * 32;       // consumer threads
-    constexpr int V = TILE / CT;      // elements per consumer thread per tile
+    constexpr int V = Op::TMA_V;      // elements per consumer thread per tile (4, or 2 when a 4 KB-per-stream
+    constexpr int TILE = CT * V;      //  stage would leave the 200 KB ring with two stages: KMAX = 10)
+    constexpr int STREAM_BYTES = TILE * 4;
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) uint64_t full[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty[MAX_STAGES];
@@ -144,12 +147,12 @@ __global__ void __launch_bounds__((CW + PW) * 32, 1) tma_kernel(Op op, int64_t n
     if constexpr (PW == 4) {
         if (producer) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-            if (tma && threadIdx.x == CT) tma_produce<Op>(ring, full, empty, s_ptr, (uint32_t)s_nlive, nv4, nstage);
+            if (tma && threadIdx.x == CT) tma_produce<Op, TILE>(ring, full, empty, s_ptr, (uint32_t)s_nlive, nv4, nstage);
             return;   // exited threads count as arrived at the barriers of the finish
         }
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     } else {
-        if (tma && threadIdx.x == CT) tma_produce<Op>(ring, full, empty, s_ptr, (uint32_t)s_nlive, nv4, nstage);
+        if (tma && threadIdx.x == CT) tma_produce<Op, TILE>(ring, full, empty, s_ptr, (uint32_t)s_nlive, nv4, nstage);
     }
     double acc[NRA];
 #pragma unroll
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__((CW + PW) * 32, 1) tma_kernel(Op op, int64_t n
                 mbar_wait(&full[stg], ph);
                 const int64_t i0 = t * TILE + (int64_t)threadIdx.x * V;
                 if (i0 < nv4) {
-                    SmemLoader ld{mine + stg * STAGE_BYTES};
+                    SmemLoader<STREAM_BYTES> ld{mine + stg * STAGE_BYTES};
                     op.template body_l<V>(ld, i0, acc);
                 }
                 __syncwarp();
@@ -220,7 +223,8 @@ inline int launch_heavy(Op op, int64_t n, bool vec, double* ws, int per_sm, int 
                         cudaStream_t s) {
     static_assert(Op::NRED <= MAXRED, "too many fused reductions");
     (void)stage_bytes;   // the ring is laid out for all NS_MAX streams of the op
-    constexpr int STAGE_BYTES = Op::NS_MAX * STREAM_BYTES;
+    constexpr int TILE = Op::TMA_CW * 32 * Op::TMA_V;
+    constexpr int STAGE_BYTES = Op::NS_MAX * TILE * 4;
     int nstage = SMEM_BUDGET / STAGE_BYTES;
     if (nstage > MAX_STAGES) nstage = MAX_STAGES;
     const bool want = tma_mode() == 1 || (tma_mode() == 0 && tma_default);
@@ -242,12 +246,12 @@ inline int launch_sel(Op op, int64_t n, bool vec, double* ws, int per_sm, int st
 
 template <int K> using KC = std::integral_constant<int, K>;
 
-// calls run(KC<4|6|8>) for FAST combinations, run(KC<8>) otherwise
+// calls run(KC<4|6|MAXM>) for FAST combinations, run(KC<MAXM>) otherwise
 #define DD4ML_RUN_K(FAST, kcap, run)                           \
     if constexpr (FAST) {                                      \
         if ((kcap) <= 4) return run(KC<4>{});                  \
         if ((kcap) <= 6) return run(KC<6>{});                  \
     }                                                          \
-    return run(KC<8>{});
+    return run(KC<DD4ML_MAXM>{});
 
 }  // namespace

@@ -308,7 +308,7 @@ def test_c4_gpt_lssr1_tr_top_level():
     ow = w0.clone()
     losses, olosses = [], []
     for _ in range(8):
-        losses.append(float(opt.step(closure)[0]))
+        losses.append(float(opt.step(closure)[0].detach()))
         olosses.append(float(oopt.step(ofg, ow)[0]))
     print(f"gpt LSSR1_TR first-order: {losses[0]:.5f} -> {losses[-1]:.5f} (oracle {olosses[-1]:.5f})")
     np.testing.assert_allclose(losses, olosses, rtol=1e-3)

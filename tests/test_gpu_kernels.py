@@ -134,6 +134,35 @@ def test_second_order_well_conditioned_within_1e5():
         assert float(pred) == pytest.approx(float(pred_or), rel=1e-4)
 
 
+@pytest.mark.parametrize("m", [6, 8, 10])
+def test_memory_lengths_up_to_the_reference_default(m):
+    """LSR1 / TR default to memory_length = 10 in the reference (lsr1.py:24, tr.py:40): the KMAX = 10
+    kernel variants, with eviction (m + 2 pairs pushed), against the oracle."""
+    torch.manual_seed(5)
+    n = 40000 + m
+    h = LSR1(gamma=1.0, memory_length=m, tol=1e-6, device=DEV)
+    hc = LSR1Memory(gamma=1.0, memory_length=m, tol=1e-6)
+    d = torch.linspace(0.5, 2.0, n)
+    for i in range(m + 2):
+        s = torch.randn(n) * 0.01
+        y = d * s
+        h.update_memory(s.to(DEV), y.to(DEV))
+        assert hc.update(s, y)
+        hc.precompute()
+    assert len(h._S) == m == len(hc)
+    assert rel_err(h.S.cpu(), torch.stack(hc.S, 1)) == 0.0
+    v = torch.randn(n)
+    assert rel_err(h.B(v.to(DEV)).cpu(), hc.B(v)) < 1e-5
+    for delta, dog in ((0.05, False), (1.0, True)):
+        g = torch.randn(n)
+        p, pred = solve_tr_second_order(g.to(DEV), torch.norm(g), delta, h, None, 1e-6, dogleg=dog)
+        p_or, pred_or = solve_second_order(g, torch.norm(g), delta, hc, 1e-6, dogleg=dog, eig_sign="canonical")
+        assert rel_err(p.cpu(), p_or) < 2e-5
+        assert float(pred) == pytest.approx(float(pred_or), rel=1e-4)
+    with pytest.raises(dd4ml_b200.DD4MLError):
+        LSR1(gamma=1.0, memory_length=11, tol=1e-6, device=DEV)
+
+
 def test_cholesky_failure_raises_like_torch():
     n = 256
     h = LSR1(gamma=1.0, memory_length=3, tol=1e-6, device=DEV)
@@ -301,4 +330,4 @@ def test_obs_wrapper_and_public_control_step():
 
 def test_memory_length_above_build_maximum_is_refused():
     with pytest.raises(dd4ml_b200.DD4MLError):
-        LSR1(memory_length=9, device=DEV)
+        LSR1(memory_length=_lib.get().max_mem_length + 1, device=DEV)

@@ -258,7 +258,7 @@ def test_apts_control_rules(shim):
     assert lib.hostshim_apts_control(hs.ptr(), 1.0, 0.95, 0.1, 1) == 1 and hs.get("delta") == pytest.approx(0.1)
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 8])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 8, 10])
 @pytest.mark.parametrize("dog", [False, True])
 def test_second_order_all_memory_sizes_vs_fp64_oracle(shim, k, dog):
     """k = 1..4 run the register-resident solvers (kspace_small.h), k >= 5 the generic ones; both
