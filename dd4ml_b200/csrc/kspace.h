@@ -309,7 +309,10 @@ KS_FN inline double step_gp(const Compact& C, const double* b, double gg, const 
     return s.cg * gg + dotk(s.c, b, C.k);
 }
 
-// register-resident variants for k <= 4 (kspace_small.h, included at the end of this file)
+// register-resident variants for k <= KS_SMALL_MAX (kspace_small.h, included at the end of this file):
+// fully unrolled, compile-time sized; k = 5 (TR's hard-coded memory length) runs 3x faster than
+// through the generic shared-memory-scratch routines (185 k -> ~60 k cycles)
+constexpr int KS_SMALL_MAX = 5;   // (6 doubles the compile time of every kernel file for a rare memory length)
 template <class T, int K>
 KS_FN bool second_order_s(dd4ml_state* st, double gn, double gg, double delta, double& cg_out, double (&c_out)[M],
                           double& pred, double& pp, double& gp);
@@ -364,13 +367,14 @@ KS_FN inline void tr_solve(dd4ml_state* st, int mode, Scratch* ws) {
         pp = S.cg * S.cg * gg;
         gp = S.cg * gg;
         st->case_id[0] = DD4ML_CASE_FIRST_ORDER;
-    } else if (k <= 4) {
+    } else if (k <= KS_SMALL_MAX) {
         bool ok;
         switch (k) {
             case 1: ok = second_order_s<T, 1>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
             case 2: ok = second_order_s<T, 2>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
             case 3: ok = second_order_s<T, 3>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
-            default: ok = second_order_s<T, 4>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
+            case 4: ok = second_order_s<T, 4>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
+            default: ok = second_order_s<T, 5>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
         }
         if (!ok) { st->solve_valid[0] = 0.0; return; }
         C.k = k;
@@ -587,13 +591,14 @@ KS_FN inline bool lsr1_try_update(dd4ml_state* st, Scratch* ws) {
     if (k == 0) {  // B = gamma I
         us = sy - gam * ss;
         uu = yy - 2.0 * gam * sy + gam * gam * ss;
-    } else if (k <= 4) {
+    } else if (k <= KS_SMALL_MAX) {
         bool ok;
         switch (k) {
             case 1: ok = update_us_uu_s<1>(st, ss, sy, yy, us, uu); break;
             case 2: ok = update_us_uu_s<2>(st, ss, sy, yy, us, uu); break;
             case 3: ok = update_us_uu_s<3>(st, ss, sy, yy, us, uu); break;
-            default: ok = update_us_uu_s<4>(st, ss, sy, yy, us, uu); break;
+            case 4: ok = update_us_uu_s<4>(st, ss, sy, yy, us, uu); break;
+            default: ok = update_us_uu_s<5>(st, ss, sy, yy, us, uu); break;
         }
         if (!ok) return false;
     } else {

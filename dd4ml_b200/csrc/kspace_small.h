@@ -1,4 +1,4 @@
-// Register-resident versions of the k-space routines for k <= 4 stored pairs (the memory
+// Register-resident versions of the k-space routines for k <= 5 (KS_SMALL_MAX) stored pairs (the memory
 // lengths of the reference's configs are 3 and 5).  Same arithmetic, same order of operations
 // as the generic routines in kspace.h, but K is a template parameter: every loop unrolls, every
 // matrix lives in registers, pivoting and sorting use predicated compare-exchanges instead of
