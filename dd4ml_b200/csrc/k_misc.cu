@@ -37,6 +37,20 @@ __global__ void __launch_bounds__(BLOCK) seg_copy_kernel(T* dst, const T* src, S
     for (int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x; i < len; i += (int64_t)gridDim.x * BLOCK) d[i] = s[i];
 }
 
+// dst[r] = src[idx[r]] for rows of `units` U-byte words: one thread per word, consecutive threads on
+// consecutive words of a row (coalesced); rows with an index outside [0, src_rows) are skipped
+template <class U>
+__global__ void __launch_bounds__(BLOCK) gather_rows_kernel(U* __restrict__ dst, const U* __restrict__ src,
+                                                            const int64_t* __restrict__ idx, int64_t nrows,
+                                                            int64_t units, int64_t src_rows) {
+    const int64_t total = nrows * units;
+    for (int64_t c = (int64_t)blockIdx.x * BLOCK + threadIdx.x; c < total; c += (int64_t)gridDim.x * BLOCK) {
+        const int64_t r = c / units, k = c - r * units;
+        const int64_t sr = __ldg(idx + r);
+        if (sr >= 0 && sr < src_rows) dst[c] = __ldg(src + sr * units + k);
+    }
+}
+
 constexpr int SET_MAX = 32;
 struct SetTable {
     int off[SET_MAX];
@@ -175,6 +189,29 @@ int dd4ml_seg_copy(void* dst, const void* src, int count, const int64_t* dst_off
         if (dtype == 0) seg_copy_kernel<float><<<grid, BLOCK, 0, s>>>((float*)dst, (const float*)src, tb);
         else seg_copy_kernel<double><<<grid, BLOCK, 0, s>>>((double*)dst, (const double*)src, tb);
     }
+    return (int)cudaGetLastError();
+}
+
+int dd4ml_gather_rows(void* dst, const void* src, const int64_t* idx, int64_t nrows, int64_t row_bytes,
+                      int64_t src_rows, void* stream) {
+    if (!dst || !src || !idx || nrows < 0 || row_bytes <= 0 || src_rows < 0) return DD4ML_E_ARG;
+    if (nrows == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | (uintptr_t)row_bytes;
+    const int64_t total_bytes = nrows * row_bytes;
+    auto grid_for_units = [&](int64_t unit) {
+        int64_t g = (total_bytes / unit + BLOCK - 1) / BLOCK;
+        const int64_t cap = (int64_t)NUM_SMS * 8;
+        return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+    };
+    if ((a & 15u) == 0)
+        gather_rows_kernel<uint4><<<grid_for_units(16), BLOCK, 0, s>>>((uint4*)dst, (const uint4*)src, idx, nrows, row_bytes / 16, src_rows);
+    else if ((a & 7u) == 0)
+        gather_rows_kernel<uint2><<<grid_for_units(8), BLOCK, 0, s>>>((uint2*)dst, (const uint2*)src, idx, nrows, row_bytes / 8, src_rows);
+    else if ((a & 3u) == 0)
+        gather_rows_kernel<uint32_t><<<grid_for_units(4), BLOCK, 0, s>>>((uint32_t*)dst, (const uint32_t*)src, idx, nrows, row_bytes / 4, src_rows);
+    else
+        gather_rows_kernel<unsigned char><<<grid_for_units(1), BLOCK, 0, s>>>((unsigned char*)dst, (const unsigned char*)src, idx, nrows, row_bytes, src_rows);
     return (int)cudaGetLastError();
 }
 

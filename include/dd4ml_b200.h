@@ -138,6 +138,13 @@ int dd4ml_seg_copy(void* dst, const void* src, int count, const int64_t* dst_off
                    const int64_t* src_off, const int64_t* lens, int64_t n_dst, int zero_fill,
                    int dtype, void* stream);
 
+/* ---- GPU-resident batch feed (dataloaders.py:18-229 samplers, trainer.py:356-382) ----------
+ * gather_rows: dst[r, :] = src[idx[r], :] for r < nrows; rows are row_bytes bytes, idx is a
+ *              DEVICE int64 vector (one epoch of sampler batches is uploaded once); rows whose
+ *              index falls outside [0, src_rows) are left untouched. */
+int dd4ml_gather_rows(void* dst, const void* src, const int64_t* idx, int64_t nrows,
+                      int64_t row_bytes, int64_t src_rows, void* stream);
+
 /* ---- LSR1.update_memory, optimizers/lsr1.py:53-144: candidate reductions in one pass (the
  * pair is written to the spare ring slot), acceptance chain + Gram/gamma update in the last CTA */
 int dd4ml_lsr1_update(double* state, double* ws, const void* s, const void* y, void* S, void* Y,

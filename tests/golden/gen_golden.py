@@ -393,7 +393,40 @@ def run_tradam(name, norm_type, lr, steps, dtype=torch.float32):
     save(name, out)
 
 
+def run_samplers(name):
+    """Batch sequences of the reference's overlap / micro-batch samplers (dataloaders.py:18-229)."""
+    import json
+    from dd4ml.dataloaders import MicroBatchFlattenSampler, MicroBatchOverlapSampler, OverlapBatchSampler
+    cases = []
+    rng = np.random.default_rng(7)
+    for n, bs, ov, drop, nsub in [(10, 4, 0.5, False, 2), (10, 4, 0.5, True, 2), (12, 4, 2, True, 3),
+                                  (12, 4, 2, False, 3), (7, 3, 0.34, False, 2), (7, 3, 1, True, 2),
+                                  (50, 16, 0.25, True, 4), (50, 16, 0.25, False, 4), (9, 5, 0.0, False, 0),
+                                  (9, 5, 0, True, 0), (5, 8, 3, False, 2), (64, 8, 7, True, 8),
+                                  (33, 10, 0.1, False, 5), (100, 25, 0.2, True, 2), (6, 2, 1, False, 3)]:
+        order = rng.permutation(n).tolist()
+        ob = OverlapBatchSampler(order, bs, overlap=ov, drop_last=drop)
+        rec = {"n": n, "batch_size": bs, "overlap": ov, "drop_last": drop, "num_subdomains": nsub, "order": order,
+               "overlap_sz": ob.overlap_sz, "len": len(ob), "batches": [list(map(int, b)) for b in ob]}
+        if nsub > 0 and ob.overlap_sz > 0:
+            try:
+                mb = MicroBatchOverlapSampler(ob, nsub, allow_empty_microbatches=False)
+                rec["micro"] = [[list(map(int, p)) for p in parts] for parts in mb]
+                rec["flat"] = [list(map(int, p)) for p in MicroBatchFlattenSampler(mb)]
+                rec["flat_len"] = len(MicroBatchFlattenSampler(mb))
+                rec["info"] = mb.get_overlap_info()
+            except (RuntimeError, ValueError) as e:
+                rec["micro_error"] = type(e).__name__
+        cases.append(rec)
+    path = os.path.join(HERE, name + ".json")
+    json.dump({"torch": torch.__version__, "cases": cases}, open(path, "w"))
+    print(f"wrote {path}  ({os.path.getsize(path) // 1024} KB)")
+
+
 def main():
+    if "--only-samplers" in sys.argv:
+        run_samplers("samplers")
+        return
     if "--only-tradam" in sys.argv:
         torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
         run_tradam("tradam_inf", math.inf, 0.01, 20)
@@ -427,6 +460,7 @@ def main():
     run_pinn("apts_pinn_ws2", 2, 10, port=29609)
     run_tradam("tradam_inf", math.inf, 0.01, 20)
     run_tradam("tradam_l2", 2, 0.5, 20)
+    run_samplers("samplers")
 
 
 if __name__ == "__main__":

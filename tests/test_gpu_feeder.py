@@ -1,0 +1,66 @@
+"""GPU-resident batch feed: the row-gather kernel against torch indexing, and
+an APTS_D run fed from it against the same run fed with host-collated batches."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from _helpers import FFNN, load_golden, set_flat
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from dd4ml_b200 import APTS_D, _lib
+    from dd4ml_b200.dataloaders import DeviceBatchFeeder, MicroBatchFlattenSampler, MicroBatchOverlapSampler, OverlapBatchSampler
+
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("shape,dtype", [((1, 28, 28), torch.float32), ((3,), torch.float32), ((5,), torch.float64),
+                                         ((), torch.int64), ((7,), torch.uint8), ((3, 32, 32), torch.float32)])
+def test_gather_rows_matches_torch_indexing(shape, dtype):
+    gen = torch.Generator().manual_seed(0)
+    n = 1000
+    if dtype.is_floating_point:
+        X = torch.randn((n,) + shape, generator=gen).to(dtype)
+    else:
+        X = torch.randint(0, 100, (n,) + shape, generator=gen).to(dtype)
+    order = torch.randperm(n, generator=gen).tolist()
+    sampler = OverlapBatchSampler(order, 96, overlap=0.25, drop_last=False)
+    feeder = DeviceBatchFeeder([X], sampler, device=DEV)
+    batches = list(sampler)
+    assert len(feeder) == len(batches)
+    for i, idx in enumerate(batches):
+        (got,) = feeder.batch(i)
+        assert got.dtype == X.dtype and tuple(got.shape) == (len(idx),) + shape
+        assert torch.equal(got.cpu(), X[idx])
+    # empty and ragged cases
+    empty = DeviceBatchFeeder([X], [], device=DEV)
+    assert len(empty) == 0 and list(empty) == []
+    with pytest.raises(IndexError):
+        DeviceBatchFeeder([X], [[0, n]], device=DEV)
+    with pytest.raises(ValueError):
+        DeviceBatchFeeder([X, X[:10]], [[0]], device=DEV)
+
+
+def test_apts_d_fed_from_device_matches_host_batches():
+    g = load_golden("apts_d_tr_fo_ws1")
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    n = X.shape[0]
+    ob = OverlapBatchSampler(list(range(n)), 32, overlap=0.25, drop_last=True)
+    sampler = MicroBatchFlattenSampler(MicroBatchOverlapSampler(ob, 2))
+
+    def run(feed):
+        from test_gpu_optimizers import _apts, cfg
+        model = FFNN(36, [12, 12], 10)
+        set_flat(model, torch.from_numpy(g["w0"]))
+        opt = _apts("d", model.to(DEV), "tr", "tr", cfg(), foc=True)
+        return [float(opt.step(xb, yb)) for xb, yb in feed]
+
+    feeder = DeviceBatchFeeder([X, Y], sampler, device=DEV)
+    l0 = _lib.get().launches
+    dev_losses = run(feeder)
+    assert _lib.get().launches - l0 >= 2 * len(feeder)
+    host_losses = run((X[idx].to(DEV), Y[idx].to(DEV)) for idx in sampler)
+    assert len(dev_losses) == len(host_losses) == len(feeder) >= 4
+    assert dev_losses == host_losses
