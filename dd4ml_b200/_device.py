@@ -64,7 +64,7 @@ class DeviceState:
         self._host[:n].copy_(self.state[:n], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         self.syncs += 1
-        return Report(self.lay, self._np)
+        return Report(self.lay, self._np[:n].tolist())      # a snapshot: later reads do not change it
 
     @staticmethod
     def raise_for(err: float):

@@ -43,7 +43,12 @@ def ptr(t: torch.Tensor | None) -> int | None:
 
 
 def stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of the current CUDA stream (called before every launch: the C accessor is
+    ~20x cheaper than ``torch.cuda.current_stream().cuda_stream``)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    except AttributeError:      # private accessor renamed in some torch version
+        return torch.cuda.current_stream().cuda_stream
 
 
 _SIGS = {

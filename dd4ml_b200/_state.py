@@ -38,7 +38,7 @@ class StateLayout:
 
 
 class Report:
-    """Attribute view over a host copy (list/ndarray/tensor of doubles) of the state."""
+    """Attribute view over a host copy (list of python floats) of the state block or its report prefix."""
 
     def __init__(self, layout: StateLayout, values):
         self._l = layout
@@ -50,5 +50,5 @@ class Report:
         except KeyError:
             raise AttributeError(name)
         if c == 1:
-            return float(self._v[o])
-        return [float(x) for x in self._v[o:o + c]]
+            return self._v[o]
+        return self._v[o:o + c]

@@ -257,7 +257,12 @@ class APTS_Base(Optimizer):
 
     # ------------------------------------------------------------------ inner loops
     def _grad_norm_of(self, optim, grad):
-        gn = getattr(optim, "last_grad_norm", None)
+        # norms the optimizer's own kernels already reduced (no extra launch, no host sync)
+        # (LSSR1_TR works in the 2-norm whatever the APTS norm and reports both; TR reports its own)
+        if self.norm_type == math.inf and hasattr(optim, "last_grad_inf"):
+            gn = optim.last_grad_inf
+        else:
+            gn = getattr(optim, "last_grad_norm", None)
         if gn is None:
             gn = float(grad.norm(p=self.norm_type))
         return gn

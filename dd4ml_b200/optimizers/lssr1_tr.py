@@ -58,7 +58,7 @@ class LSSR1_TR(Optimizer):
             raise _lib.DD4MLError("dd4ml_b200 LSSR1_TR: the PMW `flat_params` path (APTS_IP) is out of scope")
         super().__init__(param_list, {"lr": lr})
         self.delta, self.min_delta, self.max_delta = delta, min_delta, max_delta
-        self.gamma = gamma
+        self._gamma0 = gamma
         self.second_order, self.dogleg = second_order, dogleg
         if self.dogleg and not self.second_order:
             raise ValueError("Dogleg is only applicable in second-order mode")
@@ -79,7 +79,7 @@ class LSSR1_TR(Optimizer):
         self._fs_version = self._fs.version
         device, dtype = self._fs.device, self._fs.dtype           # lssr1_tr.py:99-106
         self.obs = None
-        self.hess = LSR1(gamma=self.gamma, memory_length=self.mem_length, device=device, dtype=dtype,
+        self.hess = LSR1(gamma=self._gamma0, memory_length=self.mem_length, device=device, dtype=dtype,
                          tol=self.tol)
         self._ds = self.hess.ds
         self._ds.set(second_order=1.0 if self.second_order else 0.0, dogleg=1.0 if self.dogleg else 0.0,
@@ -100,8 +100,27 @@ class LSSR1_TR(Optimizer):
         self._slot = 0
         self._pushed_delta = None
         self.n_evals = 0
-        self.last_report = None
+        self._last = None
         self.last_grad_norm = None
+        self.last_grad_inf = None
+        self._last_eval_norms = (0.0, 0.0)
+
+    # lssr1_tr.py:597 keeps `self.gamma = self.hess.gamma` (a 0-d tensor) after every step; here it is
+    # materialised on demand (building a device scalar from a host float is a synchronising copy)
+    @property
+    def gamma(self):
+        return self.hess.gamma
+
+    @property
+    def last_report(self):
+        """Diagnostics of the last step (built on demand, off the step's critical path)."""
+        if self._last is None:
+            return None
+        rep, pred, rho, alpha, evals, d0 = self._last
+        return dict(gn=rep.gn, pred=pred, rho=rho, alpha=alpha, k=int(rep.k), evals=evals, d0=d0,
+                    case=int(rep.case_id), sigma=rep.sigma, pair_ok=rep.pair_ok, pair_tried=rep.pair_tried,
+                    cyc_solve=rep.cyc_solve, cyc_eigh=rep.cyc_eigh, cyc_newton=rep.cyc_newton,
+                    newton_iters=rep.newton_iters, jacobi_sweeps=rep.jacobi_sweeps)
 
     # ------------------------------------------------------------------ plumbing
     def zero_grad(self, set_to_none: bool = False) -> None:
@@ -143,7 +162,7 @@ class LSSR1_TR(Optimizer):
         vtc, wtc = _lib.dt(b["p"].dtype), _lib.dt(self._fs.dtype)
         alpha = float(alpha)
         if self._pre is not None and self._pre[0] == alpha:
-            out, self._pre = self._pre[1], None
+            out, self._last_eval_norms, self._pre = self._pre[1], self._pre[2], None
             return out
         return self._evaluate_launch(alpha, closure, read=True)
 
@@ -167,6 +186,7 @@ class LSSR1_TR(Optimizer):
         if not read:
             return loss, gs
         rep = ds.read()
+        self._last_eval_norms = (rep.out_gg, rep.out_ginf)
         return (loss, self._f(rep.eval_loss)), gs, self._f(rep.deriv)
 
     @staticmethod
@@ -271,9 +291,8 @@ class LSSR1_TR(Optimizer):
         rep = ds.read()
         DeviceState.raise_for(rep.err)
         h.absorb(rep)
-        self.gamma = h.gamma
         if rep.converged:                                           # lssr1_tr.py:509
-            self.last_grad_norm = rep.gn
+            self.last_grad_norm, self.last_grad_inf = rep.gn, rep.ginf
             if pre is not None:                                     # undo the speculative trial point
                 lib.lssr1_trial(_lib.ptr(self._fs.data), _lib.ptr(b["old_w"]), _lib.ptr(b["p"]), 0.0, n, vtc, wtc, st)
             # the reference returns before touching old_wk / prev_grad; begin has already stored
@@ -288,7 +307,8 @@ class LSSR1_TR(Optimizer):
         if pre is not None:
             n0 -= 1
             self._lt = loss_t.dtype
-            self._pre = (0.5 * self.alpha_max, ((pre[0], self._f(rep.eval_loss)), pre[1], self._f(rep.deriv)))
+            self._pre = (0.5 * self.alpha_max, ((pre[0], self._f(rep.eval_loss)), pre[1], self._f(rep.deriv)),
+                         (rep.out_gg, rep.out_ginf))
         alpha, new_f, new_g = self._strong_wolfe_line_search(f0, d0, closure, pmax)
         if self._applied_alpha != float(alpha):                       # lssr1_tr.py:605
             lib.lssr1_trial(_lib.ptr(self._fs.data), _lib.ptr(b["old_w"]), _lib.ptr(b["p"]), float(alpha), n,
@@ -316,12 +336,12 @@ class LSSR1_TR(Optimizer):
                 self.delta = min(self.max_delta, self.nu_4 * self.delta)
             else:
                 self.delta = max(self.min_delta, self.nu_3 * self.delta)
-        self.last_report = dict(gn=rep.gn, pred=float(pred), rho=rho, alpha=float(alpha), k=int(rep.k),
-                                evals=self.n_evals - n0, d0=float(d0), case=int(rep.case_id),
-                                sigma=rep.sigma, pair_ok=rep.pair_ok, pair_tried=rep.pair_tried,
-                                cyc_solve=rep.cyc_solve, cyc_eigh=rep.cyc_eigh, cyc_newton=rep.cyc_newton,
-                                newton_iters=rep.newton_iters, jacobi_sweeps=rep.jacobi_sweeps)
-        self.last_grad_norm = None
+        self._last = (rep, float(pred), rho, float(alpha), self.n_evals - n0, float(d0))
+        # the returned gradient is always that of the last evaluation: its norms came with that
+        # evaluation's report, so the caller's convergence test (apts_base.py:397) needs no reduction
+        gg, ginf = self._last_eval_norms
+        self.last_grad_norm = math.sqrt(gg) if new_g.dtype == torch.float64 else float(np.float32(math.sqrt(gg)))
+        self.last_grad_inf = ginf
         return new_loss, new_g
 
     def state_dict(self):
@@ -339,7 +359,6 @@ class LSSR1_TR(Optimizer):
         if extra is None:
             return
         self.hess.load_state_dict(extra["hess"])
-        self.gamma = self.hess.gamma
         self.delta = float(extra["delta"])
         self._pushed_delta = None
         self._pre = None
