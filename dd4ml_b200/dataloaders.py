@@ -198,3 +198,53 @@ class DeviceBatchFeeder:
     def __iter__(self):
         for i in range(len(self)):
             yield self.batch(i)
+
+
+class HostBatchPrefetcher:
+    """Host-resident (pinned) batches -> device, with the copy of batch i+1 overlapped with the
+    optimizer step on batch i: a side stream fills a ring of ``depth`` device buffers, events order
+    it against the compute stream in both directions.  ``source`` is an iterable of tuples of
+    pinned host tensors of fixed shapes (e.g. a ``DataLoader(..., pin_memory=True)``)."""
+
+    def __init__(self, source, device="cuda", depth: int = 2):
+        self.source = source
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.DD4MLError("dd4ml_b200 has no CPU path: HostBatchPrefetcher needs a CUDA device")
+        self.depth = max(2, int(depth))
+
+    def __iter__(self):
+        copy_stream = torch.cuda.Stream(self.device)
+        ring, ready, freed = [], [], []
+        it = iter(self.source)
+
+        def issue(slot, host):
+            if slot == len(ring):
+                ring.append(tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host))
+                ready.append(torch.cuda.Event())
+                freed.append(None)
+            with torch.cuda.stream(copy_stream):
+                if freed[slot] is not None:
+                    copy_stream.wait_event(freed[slot])      # the consumer of this buffer has finished
+                for d, h in zip(ring[slot], host):
+                    d.copy_(h, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        pending = []                                         # slots in flight, oldest first
+        nxt = 0
+        for _ in range(self.depth - 1):
+            host = next(it, None)
+            if host is None:
+                break
+            issue(nxt, host); pending.append(nxt); nxt = (nxt + 1) % self.depth
+        while pending:
+            slot = pending.pop(0)
+            host = next(it, None)
+            if host is not None:                             # keep the pipe full before handing out
+                issue(nxt, host); pending.append(nxt); nxt = (nxt + 1) % self.depth
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ready[slot])
+            yield ring[slot]
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            freed[slot] = ev

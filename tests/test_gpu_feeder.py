@@ -64,3 +64,21 @@ def test_apts_d_fed_from_device_matches_host_batches():
     host_losses = run((X[idx].to(DEV), Y[idx].to(DEV)) for idx in sampler)
     assert len(dev_losses) == len(host_losses) == len(feeder) >= 4
     assert dev_losses == host_losses
+
+
+def test_host_batch_prefetcher_delivers_every_batch_in_order():
+    from dd4ml_b200.dataloaders import HostBatchPrefetcher
+    gen = torch.Generator().manual_seed(1)
+    host = [(torch.randn(257, 33, generator=gen).pin_memory(), torch.randint(0, 9, (257,), generator=gen).pin_memory())
+            for _ in range(7)]
+    seen = []
+    for xb, yb in HostBatchPrefetcher(host, DEV, depth=2):
+        assert xb.is_cuda and yb.is_cuda
+        # consume on the compute stream with some work in between, as an optimizer step would
+        seen.append((xb.clone(), yb.clone()))
+        torch.mm(torch.ones(512, 512, device=DEV), torch.ones(512, 512, device=DEV))
+    assert len(seen) == len(host)
+    for (xd, yd), (xh, yh) in zip(seen, host):
+        assert torch.equal(xd.cpu(), xh) and torch.equal(yd.cpu(), yh)
+    assert list(HostBatchPrefetcher([], DEV)) == []
+    assert len(list(HostBatchPrefetcher(host[:1], DEV, depth=3))) == 1
