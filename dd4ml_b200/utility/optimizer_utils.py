@@ -67,6 +67,10 @@ def get_loc_tr_hparams(config):                     # optimizer_utils.py:131-151
     return _tr(config, _radius_scale(config), _TR_LOC, config.loc_second_order, config.loc_dogleg)
 
 
+def get_loc_tradam_hparams(config):                 # optimizer_utils.py:154-164
+    return {"lr": config.learning_rate, "betas": (0.9, 0.999), "eps": 1e-8, "norm_type": config.norm_type}
+
+
 def ensure_tensor(d, device):
     if torch.is_tensor(d):
         return d.to(device)

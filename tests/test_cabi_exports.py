@@ -68,6 +68,9 @@ def test_hparam_tables_match_reference_values():
     assert l["sync"] is False and l["delta"] == c.delta
     c.norm_type = math.inf
     assert get_loc_tr_hparams(c)["delta"] == c.delta
+    from dd4ml_b200.utility.optimizer_utils import get_loc_tradam_hparams
+    c.learning_rate = 0.02
+    assert get_loc_tradam_hparams(c) == {"lr": 0.02, "betas": (0.9, 0.999), "eps": 1e-8, "norm_type": math.inf}
 
 
 def test_install_overlays_reference_module_paths(monkeypatch):
