@@ -281,9 +281,13 @@ class LSSR1_TR(Optimizer):
         lib.lssr1_begin(ds.sp, ds.wp, _lib.ptr(self._fs.data), _lib.ptr(b["old_w"]), _lib.ptr(g),
                         _lib.ptr(b["prev_g"]), 1 if self._has_prev else 0, h.S_ptr, h.Y_ptr,
                         _lib.ptr(loss_t), _lib.dt(loss_t.dtype), n, h.ld, vtc, htc, wtc, self.mem_length, st)
-        lib.tr_apply(ds.sp, ds.wp, _lib.ptr(g), h.S_ptr, h.Y_ptr, _lib.ptr(b["p"]), None, n, h.ld, vtc, htc,
-                     wtc, self.mem_length, st)
-        self._applied_alpha = 0.0
+        # The first trial point of the line search is w_k + 1.0 p (alpha_max / 2, lssr1_tr.py:397): when
+        # it is evaluated speculatively, the direction kernel applies it on the way (w += p) instead
+        # of a separate trial launch.  (begin has just stored old_w = w_k, so w + p == old_w + 1.0 p.)
+        fuse_first = self.speculative_first_eval and 0.5 * self.alpha_max == 1.0
+        lib.tr_apply(ds.sp, ds.wp, _lib.ptr(g), h.S_ptr, h.Y_ptr, _lib.ptr(b["p"]),
+                     _lib.ptr(self._fs.data) if fuse_first else None, n, h.ld, vtc, htc, wtc, self.mem_length, st)
+        self._applied_alpha = 1.0 if fuse_first else 0.0
         self._pre = None
         pre = None
         if self.speculative_first_eval:
