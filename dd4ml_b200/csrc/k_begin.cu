@@ -22,6 +22,7 @@ struct LssrBeginOp {
     int has_prev;
     const void* lossp;
     int lt;
+    double rad[3];   // delta, min_delta, max_delta pushed with this launch (rad[0] < 0: keep the state's)
     Slots<KMAX> sl;
     int spare;
     bool pair;
@@ -100,6 +101,7 @@ struct LssrBeginOp {
         st_v<V, VT>(prev_g, i, gv);
     }
     __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
+        if (rad[0] >= 0.0) { t->delta[0] = rad[0]; t->min_delta[0] = rad[1]; t->max_delta[0] = rad[2]; }
         t->gg[0] = s[0];
         t->ginf[0] = s[1];
         t->loss[0] = ld_scalar(lossp, lt);
@@ -137,12 +139,13 @@ struct LssrBeginOp {
 namespace {
 template <class HT, class VT, class WT>
 int begin_t(double* state, double* ws, const void* w, void* old_w, const void* g, void* prev_g, int has_prev, void* S,
-            void* Y, const void* loss, int lt, int64_t n, int64_t ld, int kcap, bool vec, cudaStream_t s) {
+            void* Y, const void* loss, int lt, int64_t n, int64_t ld, int kcap, bool vec, double delta, double min_delta,
+            double max_delta, cudaStream_t s) {
     constexpr bool FAST = sizeof(HT) == 4 && sizeof(VT) == 4 && sizeof(WT) == 4;
     auto run = [&](auto kc) {
         constexpr int K = decltype(kc)::value;
         LssrBeginOp<HT, VT, WT, K> op{(dd4ml_state*)state, (const WT*)w, (WT*)old_w, (const VT*)g, (VT*)prev_g,
-                                      (HT*)S, (HT*)Y, ld, has_prev, loss, lt};
+                                      (HT*)S, (HT*)Y, ld, has_prev, loss, lt, {delta, min_delta, max_delta}};
         return launch_sel<FAST>(op, n, vec, ws, K <= 4 ? 2 : 1,
                                 TILE * (int)(2 * sizeof(WT) + 2 * sizeof(VT) + 2 * K * sizeof(HT)), true, s);
     };
@@ -152,7 +155,8 @@ int begin_t(double* state, double* ws, const void* w, void* old_w, const void* g
 
 extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void* old_w, const void* g,
                                  void* prev_g, int has_prev, void* S, void* Y, const void* loss, int lt,
-                                 int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, void* stream) {
+                                 int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, double delta,
+                                 double min_delta, double max_delta, void* stream) {
     if (!state || !ws || !w || !old_w || !g || !prev_g || !S || !Y || !loss || n < 0 || kcap > DD4ML_MAXM)
         return DD4ML_E_ARG;
     if (lt != 0 && lt != 1) return DD4ML_E_DTYPE;
@@ -160,7 +164,8 @@ extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void*
     const bool vec = aligned16(w) && aligned16(old_w) && aligned16(g) && aligned16(prev_g) && aligned16(S) &&
                      aligned16(Y) && ld % 4 == 0;
 #define CALL(HT, VT, WT) \
-    return begin_t<HT, VT, WT>(state, ws, w, old_w, g, prev_g, has_prev, S, Y, loss, lt, n, ld, kcap, vec, s);
+    return begin_t<HT, VT, WT>(state, ws, w, old_w, g, prev_g, has_prev, S, Y, loss, lt, n, ld, kcap, vec, delta, \
+                               min_delta, max_delta, s);
     DT_SWITCH3(ht, vt, wt, CALL)
 #undef CALL
 }

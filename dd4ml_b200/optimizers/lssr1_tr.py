@@ -270,8 +270,10 @@ class LSSR1_TR(Optimizer):
         h.ensure_storage(n)
         loss_t = as_device_scalar(loss, dev)
         self._lt = loss_t.dtype
+        # the radius updated on the host after the previous step travels with the begin launch
+        rad = (-1.0, 0.0, 0.0)
         if self._pushed_delta != (self.delta, self.min_delta, self.max_delta):
-            ds.set(delta=float(self.delta), min_delta=float(self.min_delta), max_delta=float(self.max_delta))
+            rad = (float(self.delta), float(self.min_delta), float(self.max_delta))
             self._pushed_delta = (self.delta, self.min_delta, self.max_delta)
         st = _lib.stream()
         vtc, wtc, htc = _lib.dt(g.dtype), _lib.dt(self._fs.dtype), _lib.dt(h.dtype)
@@ -280,7 +282,7 @@ class LSSR1_TR(Optimizer):
         # the reference is an identity and is elided here.
         lib.lssr1_begin(ds.sp, ds.wp, _lib.ptr(self._fs.data), _lib.ptr(b["old_w"]), _lib.ptr(g),
                         _lib.ptr(b["prev_g"]), 1 if self._has_prev else 0, h.S_ptr, h.Y_ptr,
-                        _lib.ptr(loss_t), _lib.dt(loss_t.dtype), n, h.ld, vtc, htc, wtc, self.mem_length, st)
+                        _lib.ptr(loss_t), _lib.dt(loss_t.dtype), n, h.ld, vtc, htc, wtc, self.mem_length, *rad, st)
         # The first trial point of the line search is w_k + 1.0 p (alpha_max / 2, lssr1_tr.py:397): when
         # it is evaluated speculatively, the direction kernel applies it on the way (w += p) instead
         # of a separate trial launch.  (begin has just stored old_w = w_k, so w + p == old_w + 1.0 p.)
