@@ -105,7 +105,7 @@ class APTS_P(APTS_Base):
         if pred is not None:
             comm[self.n_global].copy_(pred)
         if evals is not None:
-            comm[self.n_global + 1] = float(evals)
+            comm[self.n_global + 1:self.n_global + 2].fill_(float(evals))   # (fill_, not item assignment: no host->device copy)
         if self._distributed:
             dist.all_reduce(comm, op=dist.ReduceOp.SUM)
         return comm

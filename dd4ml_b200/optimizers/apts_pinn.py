@@ -22,6 +22,7 @@ class APTS_PINN(APTS_D):
         self._half_overlap = self.overlap / 2.0
         self._bounds_cache = {}
         self._criterion_attrs = ["current_xt", "current_x"]
+        self._sel, self._sel_key = None, None
 
     def get_subdomain_bounds(self, idx: int):
         """apts_pinn.py:31-43."""
@@ -45,10 +46,15 @@ class APTS_PINN(APTS_D):
     def step(self, inputs, labels, inputs_d=None, labels_d=None, hNk=None):
         """apts_pinn.py:60-137."""
         idx = dist.get_rank() if dist.is_initialized() else 0
-        mask = self.get_subdomain_mask(inputs[..., 0].squeeze(), idx)
+        # boolean-mask indexing (apts_pinn.py:80-90) has a data-dependent shape, i.e. a host sync per
+        # call; the row indices of a given collocation tensor are computed once and reused
+        key = (inputs.data_ptr(), inputs._version, tuple(inputs.shape), idx)
+        if self._sel_key != key:
+            mask = self.get_subdomain_mask(inputs[..., 0].squeeze(), idx)
+            self._sel, self._sel_key = mask.nonzero().reshape(-1), key
         full_in = inputs.detach().requires_grad_(True)
-        sub_in = full_in[mask]
-        sub_lab = labels[mask] if labels is not None else None
+        sub_in = full_in.index_select(0, self._sel)
+        sub_lab = labels.index_select(0, self._sel) if labels is not None else None
         weight = int(sub_in.shape[0]) / max(int(full_in.shape[0]), 1)
         self.inputs_d = self.labels_d = None
         self.hNk = hNk

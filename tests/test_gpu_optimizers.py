@@ -404,3 +404,54 @@ def test_state_dict_resume_is_bit_identical(kind):
     assert resumed == cont
     assert torch.equal(flat_of(model2), w_cont)
     assert float(opt2.delta) == d_cont
+
+
+# ------------------------------------------------------------------------------ synchronisation audit
+@pytest.mark.parametrize("kind", ["tr_fo", "tr_so", "lssr1_so", "apts_d_tr", "apts_d_tr_so", "apts_d_lssr1", "apts_p_tr"])
+def test_no_hidden_host_synchronisation(kind):
+    """Every host synchronisation of a step is an explicit report read (DeviceState.read): torch's
+    sync-debug mode must see exactly as many synchronising calls as the read counters say
+    (no tensor.item() / float(tensor) / host->device scalar copies on the path)."""
+    import warnings
+    g = load_golden("apts_d_tr_fo_ws1")
+    X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
+    model = gpu_model(g)
+    if kind.startswith("apts"):
+        so = kind.endswith("_so") or kind.endswith("lssr1")
+        name = "lssr1_tr" if kind.endswith("lssr1") else "tr"
+        if kind.startswith("apts_p"):
+            opt = _apts("p", model, "tr", "tr", cfg(delta=0.1, min_delta=0.01, max_delta=0.5, norm_type=math.inf))
+        else:
+            opt = _apts("d", model, name, name, cfg(glob_second_order=so, glob_dogleg=so and name != "tr",
+                                                  loc_second_order=so, loc_dogleg=so and name != "tr"), foc=True)
+        states = [opt._ctl, opt.glob_opt._ds, opt.loc_opt._ds]
+        step = lambda: opt.step(X, Y)                                   # noqa: E731
+    else:
+        if kind.startswith("tr"):
+            opt = TR(model.parameters(), **get_tr_hparams(cfg(delta=0.1, min_delta=1e-3, max_delta=2.0,
+                                                              glob_second_order=kind == "tr_so")))
+        else:
+            hp = get_lssr1_tr_hparams(cfg(glob_second_order=True, glob_dogleg=True))
+            hp["sync"] = False
+            opt = LSSR1_TR(model.parameters(), **hp)
+        closure = make_closure(opt, model, X, Y)
+        states = [opt._ds]
+        step = lambda: opt.step(closure)                                # noqa: E731
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    reads0 = sum(s.syncs for s in states)
+    torch.cuda.set_sync_debug_mode("warn")
+    try:
+        with warnings.catch_warnings(record=True) as wl:
+            warnings.simplefilter("always")
+            for _ in range(4):
+                step()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    flagged = sum("synchroniz" in str(w.message).lower() for w in wl)
+    reads = sum(s.syncs for s in states) - reads0
+    print(f"{kind}: {reads} report reads, {flagged} synchronising calls seen by torch in 4 steps")
+    assert flagged == reads
+    if kind in ("apts_d_tr", "apts_d_tr_so", "apts_p_tr"):
+        assert reads == 4          # device-control mode: one read per OUTER iteration
