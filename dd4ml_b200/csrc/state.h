@@ -29,6 +29,9 @@
     X(gBg, 1) X(dogleg_branch, 1) X(deriv, 1) X(eval_loss, 1) X(pmax, 1)              \
     X(foc_dd, 1) X(foc_rd, 1) X(steps, 1) X(solve_valid, 1) X(gen, 1) X(aux, 1)      \
     X(cyc_solve, 1) X(cyc_eigh, 1) X(cyc_newton, 1) X(cyc_update, 1) X(jacobi_sweeps, 1) \
+    /* err_seen: last non-zero err since the host cleared it (sync-free modes read late);       */ \
+    /* inner_err: err_seen of the global / local optimizer, linked into the APTS control block  */ \
+    X(err_seen, 1) X(inner_err, 2)                                                    \
     X(report_end, 1)                                                                  \
     /* ---- L-SR1 ring bookkeeping and Gram blocks ---- */                            \
     X(spare, 1) X(order, DD4ML_MAXM)                                                  \

@@ -256,6 +256,7 @@ __device__ __forceinline__ void finish_reduce(Op& op, double* acc, double* ws) {
                 if (threadIdx.x == 0) {
                     *ticket = 0u;
                     op.finalize(s_sum, &s_scratch, &s_state);
+                    if (s_state.err[0] != 0.0) s_state.err_seen[0] = s_state.err[0];
                 }
                 __syncthreads();
                 for (int i = threadIdx.x; i < NST; i += NW * 32) gst[i] = sst[i];
@@ -263,6 +264,8 @@ __device__ __forceinline__ void finish_reduce(Op& op, double* acc, double* ws) {
                 if (threadIdx.x == 0) {
                     *ticket = 0u;
                     op.finalize(s_sum, &s_scratch, op.state());
+                    dd4ml_state* gs = op.state();
+                    if (gs != nullptr && gs->err[0] != 0.0) gs->err_seen[0] = gs->err[0];
                 }
             }
         }

@@ -312,7 +312,18 @@ class APTS_Base(Optimizer):
         return (out, b["g0"]) + self._read_control()
 
     def _read_control(self):
+        if self._device_control:
+            # numerical failures of the inner optimizers (their blocks are not read in this mode)
+            # ride on the one report read of the iteration
+            lay, lib, st = self._ctl.lay, self._ctl.lib, _lib.stream()
+            src, dst = lay.off("err_seen"), lay.off("inner_err")
+            lib.state_link(self._ctl.sp, dst, self.glob_opt._ds.sp, src, 1.0, -math.inf, math.inf, st)
+            lib.state_link(self._ctl.sp, dst + 1, self.loc_opt._ds.sp, src, 1.0, -math.inf, math.inf, st)
         rep = self._ctl.read()
+        if self._device_control and (rep.inner_err[0] or rep.inner_err[1]):
+            self.glob_opt._ds.set(err_seen=0.0)
+            self.loc_opt._ds.set(err_seen=0.0)
+            DeviceState.raise_for(rep.inner_err[0] or rep.inner_err[1])
         self.delta = rep.delta
         self._ctl_pushed["delta"] = float(rep.delta)
         self.update_pytorch_lr()

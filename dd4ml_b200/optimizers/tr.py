@@ -296,7 +296,9 @@ class TR(Optimizer):
         """Read the report block once (device-control mode): refreshes delta / L-SR1 mirrors and raises
         pending numerical errors."""
         rep = self._ds.read()
-        DeviceState.raise_for(rep.err)
+        if rep.err_seen:
+            self._ds.set(err_seen=0.0)
+        DeviceState.raise_for(rep.err_seen or rep.err)
         self._absorb(rep)
         return rep
 

@@ -88,7 +88,7 @@ def test_tr_matches_oracle_and_reference(name, so, dog, norm):
         w_before = flat_of(model)
         loss, grad = opt.step(closure)
         oloss, _ = oopt.step(ofg, ow)
-        losses.append(float(loss)); deltas.append(float(opt.delta)); olosses.append(float(oloss))
+        losses.append(float(loss.detach())); deltas.append(float(opt.delta)); olosses.append(float(oloss))
         if first_div is None and (abs(deltas[-1] - oopt.delta) > 1e-9 or rel_err(flat_of(model), ow) > 1e-3):
             first_div = i
         if i == 0:      # per-step vector parity on identical inputs
@@ -455,3 +455,30 @@ def test_no_hidden_host_synchronisation(kind):
     assert flagged == reads
     if kind in ("apts_d_tr", "apts_d_tr_so", "apts_p_tr"):
         assert reads == 4          # device-control mode: one read per OUTER iteration
+
+
+def test_device_control_surfaces_inner_numerical_failures():
+    """Sync-free APTS_D (TR/TR, second order): a Cholesky failure inside a LOCAL TR step is raised
+    by the one report read of the outer iteration, as torch.linalg.cholesky would (obs.py:65)."""
+    g = load_golden("apts_d_tr_fo_ws1")
+    X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
+    model = gpu_model(g)
+    opt = _apts("d", model, "tr", "tr", cfg(glob_second_order=True, loc_second_order=True), foc=True)
+    assert opt._device_control
+    for _ in range(3):
+        opt.step(X, Y)
+    h = opt.loc_opt.hess
+    rep = h.ds.read(full=True)
+    k = int(rep.k)
+    assert k >= 2
+    ms = h.ds.lay.maxs
+    order = [int(x) for x in rep.order[:k]]
+    YY = np.array(rep.YY).reshape(ms, ms)
+    YY[order[1], order[1]] = -abs(YY[order[0], order[0]]) * 1e6      # Psi^T Psi far from positive definite
+    h.ds.set_array("YY", YY.ravel())
+    with pytest.raises(torch.linalg.LinAlgError):
+        opt.step(X, Y)
+    # the flag is consumed: a repaired memory steps again
+    YY[order[1], order[1]] = rep.YY[order[1] * ms + order[1]]
+    h.ds.set_array("YY", YY.ravel())
+    opt.step(X, Y)
