@@ -133,12 +133,15 @@ class APTS_Base(Optimizer):
         """TR/TR configurations run an outer iteration with ONE host read at its end: the inner TR
         steps, the control step and the radius hand-over between the APTS / global / local state
         blocks all stay on the device (DD4ML_B200_DEVICE_CONTROL=0 restores one read per step)."""
-        on = (os.environ.get("DD4ML_B200_DEVICE_CONTROL", "1") != "0" and type(self.glob_opt) is TR
-              and type(self.loc_opt) is TR and self.glob_opt._flat_params_fn is None
-              and self.loc_opt._flat_params_fn is None)
+        env_on = os.environ.get("DD4ML_B200_DEVICE_CONTROL", "1") != "0"
+        loc_tr = type(self.loc_opt) is TR and self.loc_opt._flat_params_fn is None
+        on = env_on and type(self.glob_opt) is TR and loc_tr and self.glob_opt._flat_params_fn is None
         self._device_control = on
         self.glob_opt.device_control = on if type(self.glob_opt) is TR else False
-        self.loc_opt.device_control = on if type(self.loc_opt) is TR else False
+        # a local TR never needs the host inside its loop, whatever the global optimizer is
+        # (its radius is re-derived from the global one at the end of every outer iteration)
+        if type(self.loc_opt) is TR:
+            self.loc_opt.device_control = env_on and loc_tr
 
     def _link(self, dst, src, scale=1.0, lo=-math.inf, hi=math.inf):
         """dst.delta <- clamp(src.delta * scale, lo, hi) on the device."""
@@ -312,18 +315,20 @@ class APTS_Base(Optimizer):
         return (out, b["g0"]) + self._read_control()
 
     def _read_control(self):
-        if self._device_control:
-            # numerical failures of the inner optimizers (their blocks are not read in this mode)
-            # ride on the one report read of the iteration
+        # numerical failures of inner optimizers that run sync-free (their blocks are not read) ride
+        # on the control block's report read
+        inner = [(i, o) for i, o in ((0, self.glob_opt), (1, self.loc_opt)) if getattr(o, "device_control", False)]
+        if inner:
             lay, lib, st = self._ctl.lay, self._ctl.lib, _lib.stream()
             src, dst = lay.off("err_seen"), lay.off("inner_err")
-            lib.state_link(self._ctl.sp, dst, self.glob_opt._ds.sp, src, 1.0, -math.inf, math.inf, st)
-            lib.state_link(self._ctl.sp, dst + 1, self.loc_opt._ds.sp, src, 1.0, -math.inf, math.inf, st)
+            for i, o in inner:
+                lib.state_link(self._ctl.sp, dst + i, o._ds.sp, src, 1.0, -math.inf, math.inf, st)
         rep = self._ctl.read()
-        if self._device_control and (rep.inner_err[0] or rep.inner_err[1]):
-            self.glob_opt._ds.set(err_seen=0.0)
-            self.loc_opt._ds.set(err_seen=0.0)
-            DeviceState.raise_for(rep.inner_err[0] or rep.inner_err[1])
+        bad = [rep.inner_err[i] for i, _ in inner if rep.inner_err[i]]
+        if bad:
+            for _, o in inner:
+                o._ds.set(err_seen=0.0)
+            DeviceState.raise_for(bad[0])
         self.delta = rep.delta
         self._ctl_pushed["delta"] = float(rep.delta)
         self.update_pytorch_lr()

@@ -407,7 +407,8 @@ def test_state_dict_resume_is_bit_identical(kind):
 
 
 # ------------------------------------------------------------------------------ synchronisation audit
-@pytest.mark.parametrize("kind", ["tr_fo", "tr_so", "lssr1_so", "apts_d_tr", "apts_d_tr_so", "apts_d_lssr1", "apts_p_tr"])
+@pytest.mark.parametrize("kind", ["tr_fo", "tr_so", "lssr1_so", "apts_d_tr", "apts_d_tr_so", "apts_d_lssr1", "apts_p_tr",
+                                  "apts_d_mixed"])
 def test_no_hidden_host_synchronisation(kind):
     """Every host synchronisation of a step is an explicit report read (DeviceState.read): torch's
     sync-debug mode must see exactly as many synchronising calls as the read counters say
@@ -421,6 +422,10 @@ def test_no_hidden_host_synchronisation(kind):
         name = "lssr1_tr" if kind.endswith("lssr1") else "tr"
         if kind.startswith("apts_p"):
             opt = _apts("p", model, "tr", "tr", cfg(delta=0.1, min_delta=0.01, max_delta=0.5, norm_type=math.inf))
+        elif kind == "apts_d_mixed":      # LSSR1_TR global step, sync-free local TR loop
+            opt = _apts("d", model, "lssr1_tr", "tr", cfg(glob_second_order=True, glob_dogleg=True,
+                                                        loc_second_order=True), foc=True)
+            assert opt.loc_opt.device_control and not opt._device_control
         else:
             opt = _apts("d", model, name, name, cfg(glob_second_order=so, glob_dogleg=so and name != "tr",
                                                   loc_second_order=so, loc_dogleg=so and name != "tr"), foc=True)
@@ -455,6 +460,8 @@ def test_no_hidden_host_synchronisation(kind):
     assert flagged == reads
     if kind in ("apts_d_tr", "apts_d_tr_so", "apts_p_tr"):
         assert reads == 4          # device-control mode: one read per OUTER iteration
+    if kind == "apts_d_mixed":
+        assert opt.loc_opt._ds.syncs == 0 or reads <= 4 * 4      # nothing read inside the local loop
 
 
 def test_device_control_surfaces_inner_numerical_failures():
