@@ -1,13 +1,14 @@
 #pragma once
 // dd4ml_b200 -- hand-written sm_100a kernels of the trust-region hot path and their C ABI.
 //
-// Every kernel is one instance of `stream_kernel<Op>`: a persistent-grid, 128-bit
-// vectorised streaming pass over the flat n-vectors (HBM-bound; no tensor cores), with
+// Every kernel is one instance of `stream_kernel<Op>` (register staged, this file) or of
+// `tma_kernel<Op>` (TMA ring, tma.cuh): a persistent-grid, 128-bit vectorised streaming pass
+// over the flat n-vectors (HBM-bound; no tensor cores), with
 //   * up to MAXRED fused reductions accumulated in fp64 registers,
 //   * warp-shuffle -> shared-memory block reduction,
 //   * a deterministic two-stage finish: per-CTA partials + "last CTA done" ticket, the
-//     last CTA sums the partials in a fixed order and then runs the k-space routine of
-//     the op (csrc/kspace.h) from shared-memory scratch -- no host round trip.
+//     last CTA sums the partials (one warp per column, a fixed tree for a given grid) and
+//     then runs the k-space routine of the op (csrc/kspace.h) -- no host round trip.
 // The Ops below fuse what the reference does with 10-40 ATen launches per TR step.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -188,8 +189,8 @@ struct Slots {
 };
 
 // ------------------------------------------------------------------ reduction finish
-// warp shuffle -> shared memory -> per-CTA partials -> ticket; the last CTA sums the partials in
-// a fixed order (bit-reproducible) and runs the op's k-space routine.
+// warp shuffle -> shared memory -> per-CTA partials -> ticket; the last CTA sums the partials
+// with a fixed tree (bit-reproducible for a given grid) and runs the op's k-space routine.
 template <class Op, int NW = NWARP>
 __device__ __forceinline__ void finish_reduce(Op& op, double* acc, double* ws) {
     constexpr int NR = Op::NRED;

@@ -1,7 +1,7 @@
 """GPU: the bench workload (MediumFFNN n = 217 354, 5000 samples, one subdomain) with the other
 optimizer pairings of the reference's config space, to show the sync-free TR/TR path next to the
 LSSR1_TR/LSSR1_TR headline: outer iterations/s, host reads and kernel launches per iteration."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn as nn
