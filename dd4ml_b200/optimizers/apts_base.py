@@ -80,6 +80,8 @@ class APTS_Base(Optimizer):
         self._gfs = get_flat(list(model.parameters()))       # bind BEFORE the global optimizer so it reuses it
         self.device = self._gfs.device
         self.glob_opt = glob_opt(self.model.parameters(), **glob_opt_hparams)
+        if isinstance(self.glob_opt, LSSR1_TR):
+            self.glob_opt._elide_sync = True    # glob_closure_main all-reduces loss and gradient already
         self.loc_model = None
         self.loc_opt = None
         self.loc_closure = None

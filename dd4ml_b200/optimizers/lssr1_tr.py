@@ -100,6 +100,7 @@ class LSSR1_TR(Optimizer):
         self._slot = 0
         self._pushed_delta = None
         self.n_evals = 0
+        self._elide_sync = False          # set by the APTS classes (see _sync_eval)
         self._last = None
         self.last_grad_norm = None
         self.last_grad_inf = None
@@ -154,6 +155,23 @@ class LSSR1_TR(Optimizer):
     def _f(self, x):
         return np.float32(x) if self._lt == torch.float32 else np.float64(x)
 
+    # ------------------------------------------------------------------ lssr1_tr.py:175-203, 503-507, 272-276
+    def _sync_eval(self, loss_t, grad):
+        """`sync=True` on several ranks (LSSR1_TR as the top-level optimizer under DDP): the loss is
+        averaged over the ranks (in fp64, as the reference does) and rank 0's gradient is broadcast,
+        so every rank takes the same line-search decisions.  The reference also averages ||g|| and
+        g.p; here both are reduced from the broadcast gradient on the device, which is the same
+        number whenever the ranks hold the same gradient (DDP).  The APTS classes elide the whole
+        exchange for their global optimizer: their closure has already all-reduced loss and
+        gradient."""
+        if not (self.sync and self.world_size > 1) or self._elide_sync:
+            return loss_t
+        buf = loss_t.detach().to(torch.float64)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        buf /= self.world_size
+        dist.broadcast(grad, src=0)
+        return buf.to(loss_t.dtype)
+
     # ------------------------------------------------------------------ evaluations
     def _evaluate(self, alpha, closure):
         """lssr1_tr.py:247-278: move to w_k + alpha p, evaluate, directional derivative."""
@@ -175,8 +193,10 @@ class LSSR1_TR(Optimizer):
             self._applied_alpha = alpha
         loss = closure(compute_grad=True)
         self.n_evals += 1
-        loss_t = as_device_scalar(loss, self._fs.device)
         G = self._fs.flat_grad()
+        loss_t = self._sync_eval(as_device_scalar(loss, self._fs.device), G)
+        if loss_t is not loss and self.sync and self.world_size > 1 and not self._elide_sync:
+            loss = loss_t
         if G.dtype != b["p"].dtype:
             G = G.to(b["p"].dtype)
         self._slot = (self._slot + 1) % 3
@@ -268,7 +288,9 @@ class LSSR1_TR(Optimizer):
         b = self._buffers(g.dtype)
         h = self.hess
         h.ensure_storage(n)
-        loss_t = as_device_scalar(loss, dev)
+        loss_t = self._sync_eval(as_device_scalar(loss, dev), g)
+        if loss_t is not loss and self.sync and self.world_size > 1 and not self._elide_sync:
+            loss = loss_t                         # the step returns the averaged value when nothing moves
         self._lt = loss_t.dtype
         # the radius updated on the host after the previous step travels with the begin launch
         rad = (-1.0, 0.0, 0.0)
@@ -277,9 +299,6 @@ class LSSR1_TR(Optimizer):
             self._pushed_delta = (self.delta, self.min_delta, self.max_delta)
         st = _lib.stream()
         vtc, wtc, htc = _lib.dt(g.dtype), _lib.dt(self._fs.dtype), _lib.dt(h.dtype)
-        # NB lssr1_tr.py:503-507 (`sync`): on the APTS path every rank already holds identical
-        # (loss, ||g||, g) because the global closure all-reduces them, so the reduce/broadcast of
-        # the reference is an identity and is elided here.
         lib.lssr1_begin(ds.sp, ds.wp, _lib.ptr(self._fs.data), _lib.ptr(b["old_w"]), _lib.ptr(g),
                         _lib.ptr(b["prev_g"]), 1 if self._has_prev else 0, h.S_ptr, h.Y_ptr,
                         _lib.ptr(loss_t), _lib.dt(loss_t.dtype), n, h.ld, vtc, htc, wtc, self.mem_length, *rad, st)

@@ -165,3 +165,84 @@ def test_two_rank_apts_matches_reference(case):
         print(name, "gpu", list(gpu), "closest oracle branch", ensemble[int(np.argmin(dist_to))], "rel", min(dist_to))
         assert min(dist_to) < 1e-3, (list(gpu), ensemble)
     assert outs[0]["loss"][-1] < outs[0]["loss"][0]
+
+
+# ------------------------------------------------------------------------------ top-level LSSR1_TR, sync=True
+def _lssr1_worker(rank, ws, port, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import torch.distributed as dist
+    import torch.nn as nn
+    from _helpers import FFNN, load_golden, set_flat
+    from dd4ml_b200 import LSSR1_TR
+    from dd4ml_b200.utility.optimizer_utils import get_lssr1_tr_hparams
+    from test_gpu_optimizers import cfg
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws)
+    g = load_golden("apts_d_tr_fo_ws2")
+    dev = f"cuda:{rank}"
+    model = FFNN(36, [12, 12], 10)
+    set_flat(model, torch.from_numpy(g["w0"]))
+    model = torch.nn.parallel.DistributedDataParallel(model.to(dev), device_ids=[rank])   # averages the gradients
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    per = X.shape[0] // ws
+    Xr, Yr = X[rank * per:(rank + 1) * per].to(dev), Y[rank * per:(rank + 1) * per].to(dev)
+    hp = get_lssr1_tr_hparams(cfg(glob_second_order=False))
+    assert hp["sync"] is True                      # optimizer_utils.py:70
+    opt = LSSR1_TR(model.parameters(), **hp)
+    crit = nn.CrossEntropyLoss()
+
+    def closure(compute_grad=True):
+        opt.zero_grad()
+        loss = crit(model(Xr), Yr)                  # LOCAL loss: differs between the ranks
+        if compute_grad:
+            loss.backward()
+        return loss
+
+    losses, deltas = [], []
+    for _ in range(8):
+        loss, _ = opt.step(closure)
+        losses.append(float(loss.detach()))
+        deltas.append(float(opt.delta))
+    w = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu().numpy()
+    q.put((rank, dict(loss=losses, delta=deltas, w=w)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_top_level_lssr1_tr_sync():
+    """LSSR1_TR as the top-level optimizer under DDP with sync=True (lssr1_tr.py:503-507, 272-276): the
+    ranks see different local losses, the averaged loss drives identical decisions on every rank, and
+    the run equals the oracle on the averaged problem."""
+    import oracle
+    from _helpers import FFNN, load_golden, make_fg
+    ws = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_lssr1_worker, args=(r, ws, 29790, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get(timeout=600) for _ in range(ws))
+    for p in procs:
+        p.join(timeout=60)
+    assert np.array_equal(outs[0]["w"], outs[1]["w"]), "replicas diverged"
+    assert outs[0]["loss"] == outs[1]["loss"] and outs[0]["delta"] == outs[1]["delta"]
+    g = load_golden("apts_d_tr_fo_ws2")
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    per = X.shape[0] // ws
+    fgs = [make_fg(FFNN(36, [12, 12], 10), X[r * per:(r + 1) * per], Y[r * per:(r + 1) * per]) for r in range(ws)]
+
+    def fg(w):                                      # what DDP + sync present to the optimizer
+        outs_ = [f(w) for f in fgs]
+        return sum(o[0] for o in outs_) / ws, sum(o[1] for o in outs_) / ws
+
+    ohp = oracle.lssr1_hparams(0.1, 0.01, 1.0, mem_length=3, second_order=False, dogleg=False)
+    ohp.pop("sync")
+    oopt = oracle.LSSR1TROracle(**ohp, eig_sign="canonical")
+    ow = torch.from_numpy(g["w0"]).clone()
+    olosses = [float(oopt.step(fg, ow)[0]) for _ in range(8)]
+    np.testing.assert_allclose(outs[0]["loss"], olosses, rtol=1e-3)
+    assert float(np.linalg.norm(outs[0]["w"] - ow.numpy()) / np.linalg.norm(ow.numpy())) < 5e-3
