@@ -77,6 +77,7 @@ _SIGS = {
     "dd4ml_tradam_apply": ([c_void_p] * 6 + [c_double] * 3 + [c_int64, c_int, c_int, c_void_p], c_int),
     "dd4ml_apts_control": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int, c_void_p], c_int),
     "dd4ml_gather": ([c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int, c_void_p], c_int),
+    "dd4ml_obs_secular": ([c_int, c_double, c_void_p, c_void_p, c_int, c_double, c_double, c_int, c_void_p, c_void_p], c_int),
     "dd4ml_gather_rows": ([c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p], c_int),
     "dd4ml_seg_copy": ([c_void_p, c_void_p, c_int, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int64, c_int, c_int, c_void_p], c_int),
 }

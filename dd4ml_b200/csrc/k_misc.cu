@@ -51,6 +51,26 @@ __global__ void __launch_bounds__(BLOCK) gather_rows_kernel(U* __restrict__ dst,
     }
 }
 
+// OBS.phiBar_f / phiBar_fg / Newton (obs.py:184-254) as stand-alone calls: one thread, the same
+// routines the fused solve uses (kspace.h).  out = {f, g} (modes 0, 1) or {sigma, iterations,
+// degenerate evaluations} (mode 2).
+template <class T>
+__global__ void obs_secular_kernel(int mode, double x0, const T* Lam, const T* a, int m, double delta, double tol,
+                                   double* out) {
+    T L[DD4ML_MAXM + 1], A[DD4ML_MAXM + 1];
+    for (int j = 0; j < m; ++j) { L[j] = Lam[j]; A[j] = a[j]; }
+    if (mode == 2) {
+        int it = 0, nd = 0;
+        const T x = ks::newton<T>((T)x0, L, A, m, (T)delta, (T)tol, it, nd);
+        out[0] = (double)x; out[1] = (double)it; out[2] = (double)nd;
+    } else {
+        T f, g;
+        bool deg;
+        ks::phibar_fg<T>((T)x0, L, A, m, (T)delta, (T)tol, f, g, deg);
+        out[0] = (double)f; out[1] = (double)g; out[2] = deg ? 1.0 : 0.0;
+    }
+}
+
 constexpr int SET_MAX = 32;
 struct SetTable {
     int off[SET_MAX];
@@ -189,6 +209,16 @@ int dd4ml_seg_copy(void* dst, const void* src, int count, const int64_t* dst_off
         if (dtype == 0) seg_copy_kernel<float><<<grid, BLOCK, 0, s>>>((float*)dst, (const float*)src, tb);
         else seg_copy_kernel<double><<<grid, BLOCK, 0, s>>>((double*)dst, (const double*)src, tb);
     }
+    return (int)cudaGetLastError();
+}
+
+int dd4ml_obs_secular(int mode, double x0, const void* Lam, const void* a, int m, double delta, double tol,
+                      int dtype, double* out, void* stream) {
+    if (!Lam || !a || !out || m < 1 || m > DD4ML_MAXM + 1 || mode < 0 || mode > 2) return DD4ML_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == 0) obs_secular_kernel<float><<<1, 1, 0, s>>>(mode, x0, (const float*)Lam, (const float*)a, m, delta, tol, out);
+    else if (dtype == 1) obs_secular_kernel<double><<<1, 1, 0, s>>>(mode, x0, (const double*)Lam, (const double*)a, m, delta, tol, out);
+    else return DD4ML_E_DTYPE;
     return (int)cudaGetLastError();
 }
 

@@ -17,7 +17,7 @@ struct ProposeOp {
     int mode;
     Slots<KMAX> sl;
     __device__ dd4ml_state* state() const { return st; }
-    __device__ void setup() { sl.load(st, mode == 2 || st->second_order[0] != 0.0); }
+    __device__ void setup() { sl.load(st, mode >= 2 || st->second_order[0] != 0.0); }
     __device__ bool active() const { return true; }
     __device__ bool use_tma() const { return true; }
     __device__ void stream_desc(int s, const void*& p, int& esz) const {
@@ -54,6 +54,7 @@ struct ProposeOp {
         t->ginf[0] = s[1];
         for (int j = 0; j < sl.k; ++j) { t->Sg[sl.at(j)] = s[2 + j]; t->Yg[sl.at(j)] = s[2 + KMAX + j]; }
         if (mode == 2) ks::lsr1_B_coefs(t, scr);
+        else if (mode == 3) ks::smw_coefs(t, scr);
         else if (sl.k > 0) ks::tr_solve<HT>(t, mode, scr);   // OBS works in the dtype of Psi (obs.py:88)
         else ks::tr_solve<VT>(t, mode, scr);
     }

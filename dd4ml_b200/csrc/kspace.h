@@ -697,6 +697,36 @@ KS_FN inline void lsr1_B_coefs(dd4ml_state* st, Scratch* ws) {
     }
 }
 
+// OBS.ComputeSBySMW (obs.py:175-182) for a caller-supplied tau (read from st->tau):
+// p = -g/tau + Psi ((tau Minv + Psi^T Psi) \ Psi^T g), as coefficients of the output pass
+// (as coded in the reference, i.e. without the paper's 1/tau on the Psi term).
+KS_FN inline void smw_coefs(dd4ml_state* st, Scratch* ws) {
+    const int k = (int)st->k[0];
+    const double gam = st->gamma[0], tau = st->tau[0];
+    for (int i = 0; i < MS; ++i) { st->cS[i] = 0.0; st->cY[i] = 0.0; }
+    st->cg[0] = -1.0 / tau;
+    st->converged[0] = 0.0;
+    st->solve_valid[0] = 0.0;
+    st->err[0] = DD4ML_ERR_NONE;
+    if (k == 0) return;
+    Compact& C = ws->C;
+    build_compact(st, C);
+    double* x = ws->x;
+    for (int i = 0; i < k; ++i) {
+        const int pi = (int)st->order[i];
+        x[i] = st->Yg[pi] - gam * st->Sg[pi];
+    }
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) ws->W[i * M + j] = tau * C.Minv[i * M + j] + C.G[i * M + j];
+    if (!lu_factor(ws->W, k, ws->pw)) { st->err[0] = DD4ML_ERR_SINGULAR; return; }
+    lu_solve(ws->W, ws->pw, k, x);
+    for (int i = 0; i < k; ++i) {
+        const int pi = (int)st->order[i];
+        st->cY[pi] = x[i];
+        st->cS[pi] = -gam * x[i];
+    }
+}
+
 // rho and the accept decision of TR.step (tr.py:186-191), in the loss dtype T.
 template <class T>
 KS_FN inline bool tr_accept(double loss, double trial, double pred, double tol, double nu_dec, double* rho_out) {

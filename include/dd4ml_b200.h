@@ -57,7 +57,8 @@ int dd4ml_state_link(double* dst, int dst_off, const double* src, int src_off, d
  * propose: ||g|| (2 or inf), S^T g, Y^T g in one pass; the last CTA then solves the
  *   sub-problem in k-space (utility/optimizer_utils.py:197-307, optimizers/lsr1.py:146-198,
  *   solvers/obs.py:46-254) and leaves the step descriptor in `state`.
- *   mode 0 = TR, 1 = LSSR1_TR (clip + descent flip, lssr1_tr.py:563-587).
+ *   mode 0 = TR, 1 = LSSR1_TR (clip + descent flip, lssr1_tr.py:563-587), 2 = coefficients of
+ *   LSR1.B(v) (g = v), 3 = OBS.ComputeSBySMW for tau = state.tau (obs.py:175-182).
  * apply:   p = cg*g + sum_j cS_j S_j + cY_j Y_j;  optionally w += p  (tr.py:106-131,179).
  * decide:  rho test (tr.py:186-191); accepted: y = g_trial - g_old, candidate pair
  *   reductions, g_out <- g_trial, L-SR1 update chain + radius update in the last CTA
@@ -140,6 +141,15 @@ int dd4ml_gather(void* dst, int count, const void* const* srcs, const int64_t* o
 int dd4ml_seg_copy(void* dst, const void* src, int count, const int64_t* dst_off,
                    const int64_t* src_off, const int64_t* lens, int64_t n_dst, int zero_fill,
                    int dtype, void* stream);
+
+/* ---- OBS helpers as stand-alone calls (solvers/obs.py:184-254) ------------------------------
+ * mode 0/1: phiBar_f / phiBar_fg at sigma = x0 -> out = {phiBar, phiBar', degenerate flag};
+ * mode 2:   Newton from x0 (<= 200 iterations, |phiBar| <= tol) -> out = {sigma*, iterations,
+ *           degenerate evaluations}.  Lam, a: m = k+1 DEVICE values of dtype `dtype`; out: 3 device
+ *           doubles.  On the hot path these run inside tr_propose / lssr1_begin.
+ * ComputeSBySMW (obs.py:175-182) is tr_propose(mode = 3) with state.tau set, followed by tr_apply. */
+int dd4ml_obs_secular(int mode, double x0, const void* Lam, const void* a, int m, double delta,
+                      double tol, int dtype, double* out, void* stream);
 
 /* ---- GPU-resident batch feed (dataloaders.py:18-229 samplers, trainer.py:356-382) ----------
  * gather_rows: dst[r, :] = src[idx[r], :] for r < nrows; rows are row_bytes bytes, idx is a

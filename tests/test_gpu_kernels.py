@@ -331,3 +331,48 @@ def test_obs_wrapper_and_public_control_step():
 def test_memory_length_above_build_maximum_is_refused():
     with pytest.raises(dd4ml_b200.DD4MLError):
         LSR1(memory_length=_lib.get().max_mem_length + 1, device=DEV)
+
+
+def test_obs_stand_alone_helpers_match_oracle():
+    """OBS.phiBar_f / phiBar_fg / Newton / ComputeSBySMW (obs.py:175-254) as
+    stand-alone device calls against the same formulas evaluated with torch on the CPU."""
+    obs = dd4ml_b200.OBS()
+    for dtype, rtol in ((torch.float32, 2e-6), (torch.float64, 1e-12)):
+        Lam = torch.tensor([0.5, 1.5, 3.0, 1.0], dtype=dtype)
+        a = torch.tensor([0.3, -0.7, 0.2, 0.9], dtype=dtype)
+        delta = 0.4
+        for sigma in (0.0, 0.7, 5.0):
+            D = Lam + sigma
+            nrm = torch.norm(a / D)
+            f_ref = 1 / nrm - 1 / delta
+            g_ref = torch.sum(a ** 2 / D ** 3) / nrm ** 3
+            f, gq = obs.phiBar_fg(sigma, Lam.to(DEV), a.to(DEV), delta)
+            assert f.dtype == dtype and float(f) == pytest.approx(float(f_ref), rel=rtol)
+            assert float(gq) == pytest.approx(float(g_ref), rel=rtol)
+            assert float(obs.phiBar_f(sigma, Lam.to(DEV), a.to(DEV), delta)) == pytest.approx(float(f_ref), rel=rtol)
+        x = obs.Newton(0.0, Lam.to(DEV), a.to(DEV), delta)
+        assert abs(float(obs.phiBar_f(float(x), Lam.to(DEV), a.to(DEV), delta))) <= 1e-6
+        assert float(torch.norm(a / (Lam + float(x)))) == pytest.approx(delta, rel=1e-5)
+        # degenerate branch (obs.py:242-245): some |a_j| < tol -> (-1/delta, 1/tol), sigma creeps 200 x tol/delta
+        a0 = a.clone(); a0[1] = 1e-9
+        f, gq = obs.phiBar_fg(0.3, Lam.to(DEV), a0.to(DEV), delta)
+        assert float(f) == pytest.approx(-1 / delta, rel=1e-6) and float(gq) == pytest.approx(1e6, rel=1e-6)
+        assert float(obs.Newton(0.0, Lam.to(DEV), a0.to(DEV), delta)) == pytest.approx(200 * 1e-6 / delta, rel=1e-3)
+
+    torch.manual_seed(2)
+    n, m = 30000, 4
+    h = LSR1(gamma=1.0, memory_length=m, tol=1e-6, device=DEV)
+    hc = LSR1Memory(gamma=1.0, memory_length=m, tol=1e-6)
+    d = torch.linspace(0.5, 2.0, n)
+    for _ in range(m):
+        s = torch.randn(n) * 0.01
+        h.update_memory(s.to(DEV), (d * s).to(DEV))
+        assert hc.update(s, d * s)
+        hc.precompute()
+    g = torch.randn(n)
+    for tau in (1.0, 3.7):
+        Psi, Minv = hc.Psi.double(), hc.Minv.double()
+        W = tau * Minv + Psi.t() @ Psi
+        p_ref = -g.double() / tau + Psi @ torch.linalg.solve(W, Psi.t() @ g.double())
+        p = obs.ComputeSBySMW(tau, g.to(DEV), None, h, None, None)
+        assert rel_err(p.cpu(), p_ref) < 1e-5
