@@ -160,6 +160,16 @@ class APTS_Base(Optimizer):
             self._bufs_version = ver
         return self._bufs
 
+    def _update_param_group(self):                       # apts_base.py:167-170
+        for key in self.param_groups[0].keys():
+            if key != "params" and hasattr(self, key):
+                self.param_groups[0][key] = getattr(self, key)
+
+    def _sync_attributes_from_param_group(self):         # apts_base.py:172-175
+        for key, value in self.param_groups[0].items():
+            if key != "params":
+                setattr(self, key, value)
+
     def update_pytorch_lr(self) -> None:
         for g in self.param_groups:
             g["lr"] = self.delta
