@@ -49,3 +49,56 @@ def test_constructor_errors_match_reference():
     assert list(OverlapBatchSampler([], 4, overlap=1)) == []
     mb = MicroBatchOverlapSampler(ob, 7, allow_empty_microbatches=True)
     assert any(len(p) == 0 for parts in mb for p in parts)
+
+
+# ------------------------------------------------------------------ property test against a naive restatement
+def _naive_batches(order, bs, ov_sz, drop_last):
+    """Element-by-element restatement of dataloaders.py:57-96 (loops, modular indexing)."""
+    n = len(order)
+    if n == 0:
+        return []
+    nb = n // bs if drop_last else -(-n // bs)
+    out = []
+    for b in range(nb):
+        start, end = b * bs, min(b * bs + bs, n)
+        uniq = [order[i] for i in range(start, end)]
+        if not drop_last and end >= n and len(uniq) < bs:
+            out.append(uniq)
+            continue
+        if ov_sz > 0:
+            if drop_last and b == nb - 1:
+                extra = [order[i] for i in range(ov_sz)]
+            else:
+                extra = [order[(end % n + i) % n] for i in range(ov_sz)]
+            uniq = uniq + extra
+        out.append(uniq)
+    return out
+
+
+def test_overlap_sampler_matches_naive_restatement_on_random_cases():
+    import random
+    rnd = random.Random(11)
+    for _ in range(300):
+        n = rnd.randint(0, 60)
+        bs = rnd.randint(1, 20)
+        overlap = rnd.choice([0, 0.0, rnd.random(), rnd.randint(1, 25), 1.5])
+        drop = rnd.random() < 0.5
+        order = list(range(n))
+        rnd.shuffle(order)
+        frac = isinstance(overlap, float) and 0.0 < overlap < 1.0
+        if frac and int(round(overlap * bs)) >= bs:       # dataloaders.py:44-45 refuses it
+            with pytest.raises(ValueError):
+                OverlapBatchSampler(order, bs, overlap=overlap, drop_last=drop)
+            continue
+        ob = OverlapBatchSampler(order, bs, overlap=overlap, drop_last=drop)
+        assert 0 <= ob.overlap_sz < bs
+        got = [list(b) for b in ob]
+        assert got == _naive_batches(order, bs, ob.overlap_sz, drop), (n, bs, overlap, drop)
+        assert len(got) == len(ob)
+        if ob.overlap_sz > 0 and n >= bs:
+            nsub = rnd.randint(1, bs + ob.overlap_sz)
+            mb = MicroBatchOverlapSampler(ob, nsub, allow_empty_microbatches=True)
+            for parts, batch in zip(mb, got):
+                nu = min(len(batch), bs)
+                assert sorted(x for p in parts for x in p) == sorted(batch)          # a partition of the mini-batch
+                assert all(p == batch[:nu][j::nsub] + batch[nu:][j::nsub] for j, p in enumerate(parts))
