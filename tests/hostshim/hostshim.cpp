@@ -32,6 +32,21 @@ int hostshim_apts_control(double* st, double f0, double ft, double pred, int is_
     return (is_float ? ks::apts_control<float>((dd4ml_state*)st, f0, ft, pred)
                      : ks::apts_control<double>((dd4ml_state*)st, f0, ft, pred)) ? 1 : 0;
 }
+void hostshim_smw_coefs(double* st) { ks::Scratch ws; ks::smw_coefs((dd4ml_state*)st, &ws); }
+void hostshim_B_coefs(double* st) { ks::Scratch ws; ks::lsr1_B_coefs((dd4ml_state*)st, &ws); }
+// OBS.phiBar_fg (mode 1) / Newton (mode 2) in float or double; out = 3 doubles
+void hostshim_secular(int mode, double x0, const double* Lam, const double* a, int m, double delta, double tol,
+                      int is_float, double* out) {
+    if (is_float) {
+        float L[ks::M + 1], A[ks::M + 1];
+        for (int j = 0; j < m; ++j) { L[j] = (float)Lam[j]; A[j] = (float)a[j]; }
+        if (mode == 2) { int it = 0, nd = 0; out[0] = ks::newton<float>((float)x0, L, A, m, (float)delta, (float)tol, it, nd); out[1] = it; out[2] = nd; }
+        else { float f, g; bool d; ks::phibar_fg<float>((float)x0, L, A, m, (float)delta, (float)tol, f, g, d); out[0] = f; out[1] = g; out[2] = d; }
+    } else {
+        if (mode == 2) { int it = 0, nd = 0; out[0] = ks::newton<double>(x0, Lam, a, m, delta, tol, it, nd); out[1] = it; out[2] = nd; }
+        else { double f, g; bool d; ks::phibar_fg<double>(x0, Lam, a, m, delta, tol, f, g, d); out[0] = f; out[1] = g; out[2] = d; }
+    }
+}
 int hostshim_eigh(const double* A, int k, double* w, double* V) {
     double a[ks::M * ks::M], v[ks::M * ks::M], ww[ks::M];
     for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) a[i * ks::M + j] = A[i * k + j];

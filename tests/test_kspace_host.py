@@ -79,15 +79,19 @@ class HostState:
             for slot in self.live():
                 self.v[o + slot] = float(store[slot] @ gd)
 
-    def solve(self, g, mode=0, is_float=1):
-        self.reduce_g(g)
-        self.lib.hostshim_tr_solve(self.ptr(), mode, is_float)
+    def step_vector(self, g):
+        """cg g + sum_slots cS S + cY Y: what the output pass (tr_apply) materialises."""
         gd = g.double().numpy()
         p = self.get("cg") * gd
         cS, cY = self.get("cS"), self.get("cY")
         for slot in self.live():
             p = p + cS[slot] * self.S[slot] + cY[slot] * self.Y[slot]
-        return torch.from_numpy(p)
+        return p
+
+    def solve(self, g, mode=0, is_float=1):
+        self.reduce_g(g)
+        self.lib.hostshim_tr_solve(self.ptr(), mode, is_float)
+        return torch.from_numpy(self.step_vector(g))
 
     def candidate(self, s, y):
         """Reductions of a candidate pair + store it in the spare slot."""
@@ -290,3 +294,60 @@ def test_second_order_all_memory_sizes_vs_fp64_oracle(shim, k, dog):
         assert {"A": 1, "C": 3}[info["case"]] == int(hs.get("case_id"))
         assert rel_err(p, p_or) < 1e-8
         assert hs.get("pred") == pytest.approx(float(pred_or), rel=1e-7, abs=1e-12)
+
+
+# ------------------------------------------------------------------ OBS stand-alone helpers / LSR1.B on the host build
+@pytest.mark.parametrize("k", [1, 3, 5, 8, 10])
+def test_smw_and_B_coefficients_match_dense_formulas(shim, k):
+    """kspace.h::smw_coefs (OBS.ComputeSBySMW, obs.py:175-182) and lsr1_B_coefs (LSR1.B, lsr1.py:181-198)
+    against the dense fp64 formulas on Psi = Y - gamma S."""
+    lib, lay = shim
+    torch.manual_seed(100 + k)
+    n = 400
+    d = torch.linspace(0.5, 2.0, n, dtype=torch.float64)
+    S = torch.randn(n, k, dtype=torch.float64) * 0.1
+    Y = d[:, None] * S
+    gam = 0.37
+    hs = HostState(lib, lay, m=k)
+    hs.load_pairs(S, Y, gam)
+    g = torch.randn(n, dtype=torch.float64)
+    hs.reduce_g(g)
+    Psi = Y - gam * S
+    SY = S.t() @ Y
+    Minv = torch.diag(torch.diag(SY)) + torch.tril(SY, -1) + torch.tril(SY, -1).t() - gam * (S.t() @ S)
+    Minv = Minv + 1e-6 * torch.linalg.norm(Minv) * torch.eye(k, dtype=torch.float64)
+    for tau in (0.8, 4.0):
+        hs.set(tau=tau)
+        lib.hostshim_smw_coefs(hs.ptr())
+        assert hs.get("err") == 0
+        p_ref = -g / tau + Psi @ torch.linalg.solve(tau * Minv + Psi.t() @ Psi, Psi.t() @ g)
+        assert rel_err(torch.from_numpy(hs.step_vector(g)), p_ref) < 1e-9
+    lib.hostshim_B_coefs(hs.ptr())
+    Bg = gam * g + Psi @ torch.linalg.solve(Minv, Psi.t() @ g)
+    assert rel_err(torch.from_numpy(hs.step_vector(g)), Bg) < 1e-9
+
+
+@pytest.mark.parametrize("is_float", [0, 1])
+def test_secular_equation_and_newton(shim, is_float):
+    """phiBar_fg / Newton (obs.py:210-254): regular and degenerate branches, reference iteration cap."""
+    lib, _ = shim
+    lib.hostshim_secular.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
+                                     ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                     ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    Lam = np.array([0.5, 1.5, 3.0, 1.0]); a = np.array([0.3, -0.7, 0.2, 0.9]); delta = 0.4
+    out = np.zeros(3)
+    P = lambda x: x.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
+    rtol = 2e-6 if is_float else 1e-13
+    for sigma in (0.0, 0.7, 5.0):
+        lib.hostshim_secular(1, sigma, P(Lam), P(a), 4, delta, 1e-6, is_float, P(out))
+        D = Lam + sigma
+        nrm = np.linalg.norm(a / D)
+        assert out[0] == pytest.approx(1 / nrm - 1 / delta, rel=rtol)
+        assert out[1] == pytest.approx(np.sum(a ** 2 / D ** 3) / nrm ** 3, rel=rtol) and out[2] == 0
+    lib.hostshim_secular(2, 0.0, P(Lam), P(a), 4, delta, 1e-6, is_float, P(out))
+    assert np.linalg.norm(a / (Lam + out[0])) == pytest.approx(delta, rel=1e-5) and 1 <= out[1] < 50
+    a0 = a.copy(); a0[1] = 1e-9                                   # degenerate: (-1/delta, 1/tol) for every sigma
+    lib.hostshim_secular(1, 0.3, P(Lam), P(a0), 4, delta, 1e-6, is_float, P(out))
+    assert out[0] == pytest.approx(-1 / delta, rel=1e-6) and out[1] == pytest.approx(1e6) and out[2] == 1
+    lib.hostshim_secular(2, 0.0, P(Lam), P(a0), 4, delta, 1e-6, is_float, P(out))
+    assert out[1] == 200 and out[0] == pytest.approx(200 * 1e-6 / delta, rel=1e-3)     # obs.py:217 cap
