@@ -87,6 +87,12 @@ class FlatBuffer:
     # ------------------------------------------------------------------ gradients
     def flat_grad(self) -> torch.Tensor:
         """The flat gradient of the last backward (views kept, or one gather launch)."""
+        # nn.Module._apply (.double() / .to(dtype)) swaps `param.data` AND `param.grad.data` in place:
+        # the identity test below would still pass while the view objects no longer alias the flat
+        # buffer.  A whole-model conversion always moves the first parameter: O(1) check, then rebind.
+        p0 = self.params[0]
+        if p0.data_ptr() != self._base or p0.dtype != self.dtype:
+            self.ensure()
         stale = [i for i, (p, gv) in enumerate(zip(self.params, self._gviews))
                  if p.requires_grad and p.grad is not gv]
         if stale:
@@ -117,11 +123,16 @@ class FlatBuffer:
             if self.params[i].requires_grad:
                 self.params[i].grad = self._gviews[i]
 
-    def zero_grad(self):
-        self.grad.zero_()
+    def rebind_grads(self):
+        """Point every ``p.grad`` at its flat view again (no memset): used after a CUDA-graph replay,
+        which writes the gradient through the captured views whatever ``p.grad`` currently is."""
         for p, gv in zip(self.params, self._gviews):
             if p.requires_grad and p.grad is not gv:
                 p.grad = gv
+
+    def zero_grad(self):
+        self.grad.zero_()
+        self.rebind_grads()
 
 
 class FlatSlice:
@@ -154,6 +165,9 @@ class FlatSlice:
 
     def zero_grad(self):
         self.fb.zero_grad()
+
+    def rebind_grads(self):
+        self.fb.rebind_grads()
 
 
 def get_flat(params) -> FlatSlice:

@@ -47,9 +47,12 @@ class GraphedEval:
         loss.backward(retain_graph=bool(torch.is_tensor(inputs) and inputs.requires_grad))
         return loss.detach()
 
-    @staticmethod
-    def _key(inputs, labels):
-        return (tuple(inputs.shape), inputs.dtype, tuple(labels.shape), labels.dtype)
+    def _key(self, inputs, labels):
+        # everything a captured graph bakes in besides the tensor addresses: shapes / dtypes / strides
+        # of the batch, the flat-buffer generation (a dtype or storage change re-binds the parameters:
+        # an old graph would read the orphaned storage) and train/eval mode (dropout, BatchNorm)
+        return (tuple(inputs.shape), inputs.dtype, tuple(inputs.stride()), tuple(labels.shape), labels.dtype,
+                tuple(labels.stride()), self.flat.version, self.model.training)
 
     def _capture(self, inputs, labels, private):
         e = _Entry()
@@ -79,6 +82,8 @@ class GraphedEval:
                 or not inputs.is_cuda):
             return self._eval(inputs, labels)
         key = self._key(inputs, labels)
+        if self.cache and next(iter(self.cache))[-2] != key[-2]:
+            self.cache.clear()                   # parameters were re-bound: drop every stale graph
         if key in self.failed:
             return self._eval(inputs, labels)
         e = self.cache.get(key)
@@ -96,5 +101,9 @@ class GraphedEval:
             e.static_in.copy_(inputs)
             e.static_lab.copy_(labels)
         e.graph.replay()
+        # the replay wrote the gradient into the flat views; a caller may have set p.grad to None
+        # (zero_grad(set_to_none=True)) since the capture -- re-establish the views so that
+        # flat_grad() does not take the fresh gradient for a missing one
+        self.flat.rebind_grads()
         self.replays += 1
         return e.loss.clone()

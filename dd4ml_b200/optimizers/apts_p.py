@@ -52,11 +52,9 @@ class APTS_P(APTS_Base):
         self._lfb = fb
         self._lfs = FlatSlice(fb, 0, fb.n)
         owned = [lps[i] for i in owned_idx]
-        self.n_local_owned = sum(p.numel() for p in owned)
         self.loc_opt = loc_opt(params=owned, **loc_opt_hparams)
         self.loc_closure = self.non_foc_loc_closure
-        self.n_global = self._gfs.n
-        self.n_local = self.n_local_owned
+        self._layout()
         self.sqrt_n_global = math.sqrt(self.n_global)
         self.sqrt_n_local = math.sqrt(max(self.n_local, 1))
         # apts_p.py:92-104: infinity-norm radii -> 2-norm radii of the inner optimizers
@@ -66,7 +64,22 @@ class APTS_P(APTS_Base):
         self.loc_opt.min_delta = self.glob_opt.min_delta
         self.glob_opt.delta = max(self.glob_opt.min_delta, min(self.glob_opt.max_delta, self.delta * self.sqrt_n_global))
         self.loc_opt.delta = self.glob_opt.delta
-        # segment tables: global offset <-> local offset of every tensor
+        self._has_buffers = any(True for _ in self.loc_model.buffers())
+        self._enable_device_control()
+        from ..graphs import GraphedEval
+        self._loc_eval = GraphedEval(self.loc_model, self.criterion, self._lfs)
+
+    def _layout(self):
+        """Segment tables global offset <-> local offset of every parameter tensor, and the sizes
+        derived from them.  Offsets are in elements, so they survive a dtype change; they are
+        rebuilt together with the flat buffers all the same (`_rebind`)."""
+        fb = self._lfb
+        lps = list(self.loc_model.parameters())
+        owned_idx = self._owned_idx
+        other_idx = [i for i in range(len(lps)) if i not in set(owned_idx)]
+        self.n_local_owned = sum(lps[i].numel() for i in owned_idx)
+        self.n_global = self._gfs.n
+        self.n_local = self.n_local_owned
         goff = self._gfs.fb.offsets
         order = owned_idx + other_idx
         loff = {t: fb.offsets[j] for j, t in enumerate(order)}
@@ -76,10 +89,28 @@ class APTS_P(APTS_Base):
                            mk([numel[t] for t in owned_idx]))
         self._seg_all = (len(order), mk([loff[t] for t in order]), mk([goff[t] for t in order]),
                          mk([numel[t] for t in order]))
-        self._has_buffers = any(True for _ in self.loc_model.buffers())
-        self._enable_device_control()
-        from ..graphs import GraphedEval
-        self._loc_eval = GraphedEval(self.loc_model, self.criterion, self._lfs)
+
+    def _rebind(self):
+        """The reference Trainer converts ``model`` and ``optimizer.loc_model`` to float64 AFTER the
+        optimizer exists (trainer.py:1115-1128, 1203-1211), which replaces every parameter's storage.
+        Both flat buffers are re-bound to the new storages (FlatBuffer.ensure), the segment tables and
+        the n-vector work buffers are rebuilt, and the inner optimizers pick the new buffers up
+        through their FlatSlice versions -- as APTS_D does."""
+        g_re = self._gfs.ensure()
+        l_re = self._lfb.ensure()
+        if not (g_re or l_re):
+            return False
+        if self._gfs.dtype != self._lfb.dtype:
+            raise _lib.DD4MLError(
+                f"dd4ml_b200 APTS_P: model is {self._gfs.dtype} but loc_model is {self._lfb.dtype}; convert both "
+                "(the reference Trainer does: trainer.py:1203-1211)")
+        self._layout()
+        self._buffers()
+        # the clone mirrors the global model between outer iterations: re-establish it in the new storage
+        cnt, dsto, srco, lens = self._seg_all
+        self._ctl.lib.seg_copy(_lib.ptr(self._lfb.data), _lib.ptr(self._gfs.data), cnt, dsto, srco, lens,
+                               self._lfb.n, 0, _lib.dt(self._gfs.dtype), _lib.stream())
+        return True
 
     # ------------------------------------------------------------------ flat vectors (API parity)
     @torch.no_grad()
@@ -140,9 +171,7 @@ class APTS_P(APTS_Base):
         if self._resync:                 # first step after load_state_dict
             self.sync_glob_to_loc()
             self._resync = False
-        if self._gfs.ensure() or self._lfb.ensure():
-            raise _lib.DD4MLError("dd4ml_b200 APTS_P: parameter storage changed after construction "
-                                  "(convert the model dtype before building the optimizer)")
+        self._rebind()
         b = self._buffers()
         n = self.n_global
         self.glob_opt._known_gn = self.loc_opt._known_gn = None

@@ -22,7 +22,7 @@ class APTS_PINN(APTS_D):
         self._half_overlap = self.overlap / 2.0
         self._bounds_cache = {}
         self._criterion_attrs = ["current_xt", "current_x"]
-        self._sel, self._sel_key = None, None
+        self._sel, self._sel_src, self._sel_ver = None, None, None
 
     def get_subdomain_bounds(self, idx: int):
         """apts_pinn.py:31-43."""
@@ -47,11 +47,11 @@ class APTS_PINN(APTS_D):
         """apts_pinn.py:60-137."""
         idx = dist.get_rank() if dist.is_initialized() else 0
         # boolean-mask indexing (apts_pinn.py:80-90) has a data-dependent shape, i.e. a host sync per
-        # call; the row indices of a given collocation tensor are computed once and reused
-        key = (inputs.data_ptr(), inputs._version, tuple(inputs.shape), idx)
-        if self._sel_key != key:
+        # call; the row indices are reused only while the SAME tensor object is passed unmodified
+        # (a strong reference is kept, so its address cannot be recycled for another point set)
+        if self._sel_src is not inputs or self._sel_ver != inputs._version:
             mask = self.get_subdomain_mask(inputs[..., 0].squeeze(), idx)
-            self._sel, self._sel_key = mask.nonzero().reshape(-1), key
+            self._sel, self._sel_src, self._sel_ver = mask.nonzero().reshape(-1), inputs, inputs._version
         full_in = inputs.detach().requires_grad_(True)
         sub_in = full_in.index_select(0, self._sel)
         sub_lab = labels.index_select(0, self._sel) if labels is not None else None

@@ -275,13 +275,13 @@ class LSSR1_TR(Optimizer):
     # ------------------------------------------------------------------ the step
     def step(self, closure: Callable[[], torch.Tensor], **_):
         lib, ds = self._ds.lib, self._ds
+        self._fs.ensure()                    # before reading gradients: .double() after construction
         dev = self._fs.device
         loss = _["loss"] if "loss" in _ else closure(compute_grad=True)
         g = _["grad"] if "grad" in _ else self._flatten_grads()
         g = g.detach()
         if not g.is_contiguous():
             g = g.contiguous()
-        self._fs.ensure()
         n = self._fs.n
         if g.numel() != n:
             raise _lib.DD4MLError(f"dd4ml_b200 LSSR1_TR: gradient has {g.numel()} elements, parameters {n}")

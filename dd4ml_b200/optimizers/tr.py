@@ -194,6 +194,7 @@ class TR(Optimizer):
     # ------------------------------------------------------------------ the step
     def step(self, closure, **_) -> Tuple[torch.Tensor, torch.Tensor]:
         lib, ds = self._ds.lib, self._ds
+        self._fs.ensure()                    # before reading gradients: .double() after construction
         dev = self._fs.device
         loss = _["loss"] if "loss" in _ else closure(compute_grad=True)
         grad = _["grad"] if "grad" in _ else self._flat_grad()

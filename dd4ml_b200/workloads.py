@@ -54,3 +54,61 @@ def apts_d_yaml_config(**over):
              max_loc_iters=3, max_glob_iters=1, glob_pass=True, foc=True)
     c.update(over)
     return Cfg(**c)
+
+
+class PINNNet(nn.Module):
+    """1 -> [20] x 8 -> 1 with tanh (reference models/ffnn/pinn_ffnn.py:11-29): n = 3 001 parameters,
+    18 tensors in the same order (weight, bias per layer)."""
+
+    def __init__(self, in_features=1, hidden=(20,) * 8, out_features=1):
+        super().__init__()
+        dims = [in_features, *hidden]
+        mods = []
+        for a, b in zip(dims[:-1], dims[1:]):
+            mods += [nn.Linear(a, b), nn.Tanh()]
+        mods.append(nn.Linear(dims[-1], out_features))
+        self.net = nn.Sequential(*mods)
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class AllenCahnLoss(nn.Module):
+    """Residual loss of the 1-D Allen-Cahn PINN, -u'' + u^3 - u = 0 on [low, high], u(low) = 1,
+    u(high) = -1 (reference utility/pinn_allencahn_loss.py:14-60): mean over ALL points of the squared
+    interior residual masked by (1 - flag) plus mean over all points of the squared boundary error
+    masked by flag.  ``current_x`` is the collocation tensor the prediction was computed from (set by
+    the caller: trainer.py:997-998, apts_pinn.py:_set_criterion_input)."""
+
+    def __init__(self, current_x=None, low=0.0, high=1.0):
+        super().__init__()
+        self.current_x, self.low, self.high = current_x, low, high
+
+    def forward(self, u, flag):
+        x = self.current_x
+        if x is None:
+            raise ValueError("current_x must be set before calling AllenCahnLoss")
+        if not x.requires_grad:
+            x.requires_grad_(True)
+        ones = torch.ones_like(u)
+        du, = torch.autograd.grad(u, x, ones, create_graph=True, retain_graph=True)
+        d2u, = torch.autograd.grad(du, x, torch.ones_like(du), create_graph=True)
+        flag = flag.squeeze()
+        xs, us = x.squeeze(), u.squeeze()
+        res = (-d2u + u ** 3 - u).squeeze()
+        target = torch.zeros_like(xs)
+        target[torch.isclose(xs, torch.tensor(self.low, device=x.device, dtype=x.dtype))] = 1.0
+        target[torch.isclose(xs, torch.tensor(self.high, device=x.device, dtype=x.dtype))] = -1.0
+        return (res ** 2 * (1 - flag)).mean() + ((us - target) ** 2 * flag).mean()
+
+
+def allen_cahn_points(n_interior=1000, low=0.0, high=1.0):
+    """Collocation set of datasets/pinn_allencahn.py:38-64: n_interior equispaced interior points plus
+    the two boundary points, sorted; returns (x [N,1] fp32, boundary flag [N,1] fp32)."""
+    step = (high - low) / (n_interior + 1)
+    interior = torch.linspace(low + step, high - step, n_interior, dtype=torch.float32).unsqueeze(1)
+    boundary = torch.tensor([[low], [high]], dtype=torch.float32)
+    data = torch.cat([boundary, interior], 0)
+    mask = torch.cat([torch.ones(2, 1), torch.zeros(n_interior, 1)], 0)
+    idx = torch.argsort(data[:, 0])
+    return data[idx], mask[idx]

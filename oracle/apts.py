@@ -239,7 +239,13 @@ class APTSPOracle(_APTSBase):
 
     def __init__(self, w_init, owned, glob_kind, glob_hp, loc_kind, loc_hp, *, delta, min_delta,
                  max_delta, nu_dec, nu_inc, inc_factor, dec_factor, glob_pass=True,
-                 max_loc_iters=3, max_glob_iters=3, tol=1e-6, eig_sign="lapack"):
+                 max_loc_iters=3, max_glob_iters=3, tol=1e-6, eig_sign="lapack", ctor_dtype=None):
+        # ctor_dtype: dtype the model had when the reference optimizer was CONSTRUCTED, if it was
+        # converted afterwards (trainer.py:1203-1211).  `_step_buffer` (apts_p.py:108) and, without flat
+        # hooks, the global optimizer's flat buffers keep that dtype and round what passes through.
+        self.ctor_dtype = ctor_dtype
+        if ctor_dtype is not None and glob_kind == "lssr1_tr":
+            glob_hp = dict(glob_hp, buf_dtype=ctor_dtype)
         super().__init__(w_init, len(owned), glob_kind, glob_hp, loc_kind, loc_hp, delta=delta,
                          min_delta=min_delta, max_delta=max_delta, nu_dec=nu_dec, nu_inc=nu_inc,
                          inc_factor=inc_factor, dec_factor=dec_factor, glob_pass=glob_pass,
@@ -284,7 +290,10 @@ class APTSPOracle(_APTSBase):
         merged = torch.zeros_like(w0)                               # apts_p.py:115-153
         for r in range(R):
             merged[self.owned[r]] = self.w_loc[r][self.owned[r]]
-        step = (merged - w0).clamp_(min=-self.delta, max=self.delta)   # :221-224
+        step = merged - w0
+        if self.ctor_dtype is not None:
+            step = step.to(self.ctor_dtype)                         # torch.sub(..., out=self._step_buffer)
+        step = step.clamp_(min=-self.delta, max=self.delta)         # :221-224
         pred = reds[0].clone()
         for r in range(1, R):
             pred = pred + reds[r]

@@ -41,7 +41,7 @@ class LSSR1TROracle:
                  max_zoom_iters=5, mu=0.9, tau_1=0.1, tau_2=0.25, tau_3=0.75, nu_1=0.25,
                  nu_2=0.5, nu_3=0.8, nu_4=1.2, tol=1e-8, norm_type=2, c_1=1e-4, c_2=0.9,
                  alpha_max=10.0, sync=False, paper_tr_update=True, dtype=torch.float32,
-                 eig_sign="lapack"):
+                 eig_sign="lapack", buf_dtype=None):
         if dogleg and not second_order:
             raise ValueError("Dogleg is only applicable in second-order mode")
         self.lr, self.delta, self.min_delta, self.max_delta = lr, delta, min_delta, max_delta
@@ -54,6 +54,11 @@ class LSSR1TROracle:
         self.paper_tr_update = bool(paper_tr_update)
         self.hess = LSR1Memory(gamma=gamma, memory_length=mem_length, tol=self.tol, dtype=dtype)
         self.eig_sign = eig_sign
+        # lssr1_tr.py:99-142, 205-229: without flat hooks the parameters and every evaluated
+        # gradient pass through `flat_wk` / `flat_gk`, allocated in the dtype the first parameter had
+        # AT CONSTRUCTION.  When the model is converted afterwards (the Trainer's .double(),
+        # trainer.py:1203-1211) they are rounded to that dtype: pass it as ``buf_dtype``.
+        self.buf_dtype = buf_dtype
         self.vk = None
         self.old_wk = None
         self.prev_grad = None
@@ -64,6 +69,8 @@ class LSSR1TROracle:
     def _eval(self, fg, w, wk, p, alpha):
         w.copy_(wk + alpha * p)
         loss, grad = fg(w)
+        if self.buf_dtype is not None:
+            grad = grad.to(self.buf_dtype)                # _flatten_grads through flat_gk
         self.n_evals += 1
         return loss, grad, grad.dot(p.to(grad.dtype))
 
@@ -121,7 +128,7 @@ class LSSR1TROracle:
         if gn <= self.tol:
             rec["converged"] = True
             return loss, g
-        wk = w.clone()
+        wk = w.clone() if self.buf_dtype is None else w.to(self.buf_dtype)   # _flatten_params through flat_wk
         updated = False
         if self.second_order and self.prev_grad is not None:          # :518-524
             sk, yk = wk - self.old_wk, g - self.prev_grad
@@ -138,7 +145,7 @@ class LSSR1TROracle:
             p_star, pred = solve_first_order(g, gn, self.delta, self.tol)
         # dead momentum (:552-561): vk = mu*vk + (wk - old_wk) with old_wk == wk
         if self.vk is None:
-            self.vk = torch.zeros_like(wk)
+            self.vk = torch.zeros_like(wk)                             # flat_vk: the buffer dtype
         vk = self.vk
         vk.mul_(self.mu).add_(wk - self.old_wk)
         vk_sq = vk.dot(vk)

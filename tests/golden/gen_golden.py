@@ -306,6 +306,137 @@ def run_pinn(name, ws, steps, port=29631):
     save(name, out)
 
 
+# ------------------------------------------------------------------ BASELINE config 5 as the Trainer runs it
+def _config5_worker(rank, ws, port, glob, loc, paper, delta, min_delta, max_delta, steps, q):
+    """PINNFFNN + AllenCahnPINNLoss + APTS_P exactly as `Trainer.run_by_epoch_PINN` /
+    `_train_one_batch_PINN` drive them (trainer.py:985-1002, 1203-1214): everything is BUILT in
+    float32, then `model` and `optimizer.loc_model` are converted to float64 and the optimizer is
+    stepped with double inputs that require grad and the boundary mask as (double) labels."""
+    from dd4ml.datasets.pinn_allencahn import AllenCahn1DDataset
+    from dd4ml.models.ffnn.pinn_ffnn import PINNFFNN
+    from dd4ml.utility.pinn_allencahn_loss import AllenCahnPINNLoss
+    torch.set_num_threads(1)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    set_seed(42)
+    ds = AllenCahn1DDataset(AllenCahn1DDataset.get_default_config())
+    model = PINNFFNN(PINNFFNN.get_default_config())
+    crit = AllenCahnPINNLoss()
+    cfg = CfgNode(delta=delta, min_delta=min_delta, max_delta=max_delta, norm_type=math.inf,
+                  glob_second_order=False, glob_dogleg=False, loc_second_order=False, loc_dogleg=False,
+                  mem_length=5, max_wolfe_iters=5, max_zoom_iters=5, tol=1e-6, paper_tr_update=paper,
+                  glob_opt=glob, loc_opt=loc, learning_rate=0.1)
+    cfg = APTS_P.setup_APTS_hparams(cfg)
+    opt = APTS_P(model.parameters(), model=model, criterion=crit, device="cpu", nr_models=ws,
+                 glob_opt=cfg.glob_opt, glob_opt_hparams=cfg.glob_opt_hparams, loc_opt=cfg.loc_opt,
+                 loc_opt_hparams=cfg.loc_opt_hparams, glob_pass=True, norm_type=math.inf, max_loc_iters=3,
+                 max_glob_iters=1, tol=1e-6, **cfg.apts_params)
+    out = {"w0_f32": flat(model).numpy()}
+    model = model.double()                                   # trainer.py:1203
+    opt.loc_model = opt.loc_model.double()                   # trainer.py:1211
+    x = ds.data.double()                                     # trainer.py:987-989
+    y = ds.boundary_mask.double()
+    x.requires_grad_(True)
+    crit.current_x = x                                       # trainer.py:997-998
+    out.update(x=x.detach().numpy(), y=y.numpy(),
+               owned_tensors=np.asarray(sorted(int(i) for i in opt.loc_model._trainable_indices)))
+    losses, deltas, gdeltas, ldeltas, gevals, ws_hist = [], [], [], [], [], []
+    for _ in range(steps):
+        loss = opt.step(inputs=x, labels=y)
+        losses.append(float(loss))
+        deltas.append(float(opt.delta))
+        gdeltas.append(float(opt.glob_opt.delta))
+        ldeltas.append(float(opt.loc_opt.delta))
+        gevals.append(float(opt.grad_evals))
+        ws_hist.append(flat(model).numpy())
+    out.update(loss=np.asarray(losses), delta=np.asarray(deltas), glob_delta=np.asarray(gdeltas),
+               loc_delta=np.asarray(ldeltas), grad_evals=np.asarray(gevals),
+               w_step1=ws_hist[0], w_step3=ws_hist[2], w_final=ws_hist[-1])
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_config5(name, ws, glob, loc, paper, steps, port, delta=0.1, min_delta=0.01, max_delta=0.5):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_config5_worker,
+                         args=(r, ws, port, glob, loc, paper, delta, min_delta, max_delta, steps, q))
+             for r in range(ws)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get() for _ in range(ws))
+    for p in procs:
+        p.join()
+    out = outs[0]
+    for r in range(ws):
+        out[f"owned_tensors_rank{r}"] = outs[r]["owned_tensors"]
+    for r in range(1, ws):
+        assert np.array_equal(outs[r]["w_final"], out["w_final"]), "ranks diverged"
+    meta(out, steps=steps, world_size=ws, glob=glob, loc=loc, paper_tr_update=int(paper), delta0=delta,
+         min_delta=min_delta, max_delta=max_delta, kind="apts_p_config5")
+    save(name, out)
+
+
+def _pinn_literal_worker(rank, ws, port, steps, q):
+    """tests/test_pinn_subdomains.py:141-204 (`_run_apts_pinn`) literally, plus a seed."""
+    from dd4ml.datasets.pinn_allencahn import AllenCahn1DDataset
+    from dd4ml.models.ffnn.pinn_ffnn import PINNFFNN
+    from dd4ml.utility.pinn_allencahn_loss import AllenCahnPINNLoss
+    torch.set_num_threads(1)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    set_seed(42)
+    ds = AllenCahn1DDataset(AllenCahn1DDataset.get_default_config())
+    model = PINNFFNN(PINNFFNN.get_default_config())
+    crit = AllenCahnPINNLoss()
+    tr_kw = dict(delta=0.1, nu_dec=0.25, nu_inc=0.75, inc_factor=1.2, dec_factor=0.9, max_delta=2.0,
+                 min_delta=1e-3, tol=1e-6)
+    opt = APTS_PINN(model.parameters(), model=model, criterion=crit, device="cpu", glob_opt=TR,
+                    glob_opt_hparams=tr_kw, loc_opt=TR, loc_opt_hparams=tr_kw, glob_pass=False, foc=False,
+                    norm_type=2, max_loc_iters=10, max_glob_iters=1, num_subdomains=ws, **tr_kw)
+    x = ds.data
+    flag = torch.cat([torch.zeros(len(ds.x_interior), 1), torch.ones(len(ds.x_boundary), 1)])
+    crit.current_x = x
+    out = {"w0": flat(model).numpy(), "x": x.numpy(), "flag": flag.numpy()}
+    losses, deltas, gevals, ws_hist = [], [], [], []
+    for _ in range(steps):
+        loss = opt.step(inputs=x, labels=flag)
+        losses.append(float(loss))
+        deltas.append(float(opt.delta))
+        gevals.append(float(opt.grad_evals))
+        ws_hist.append(flat(model).numpy())
+    out.update(loss=np.asarray(losses), delta=np.asarray(deltas), grad_evals=np.asarray(gevals),
+               w_step1=ws_hist[0], w_step3=ws_hist[2], w_final=ws_hist[-1])
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_pinn_literal(name, ws, steps, port):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pinn_literal_worker, args=(r, ws, port, steps, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get() for _ in range(ws))
+    for p in procs:
+        p.join()
+    out = outs[0]
+    for r in range(1, ws):
+        assert np.array_equal(outs[r]["w_final"], out["w_final"]), "ranks diverged"
+    meta(out, steps=steps, world_size=ws, kind="apts_pinn_literal")
+    save(name, out)
+
+
+def run_config5_all():
+    run_config5("config5_apts_p_tr_ws2", 2, "tr", "tr", False, 12, 29641)
+    run_config5("config5_apts_p_lssr1_ws2", 2, "lssr1_tr", "lssr1_tr", True, 12, 29642)
+    run_config5("config5_apts_p_tr_small_ws2", 2, "tr", "tr", False, 12, 29643, delta=0.002, min_delta=1e-5,
+                max_delta=0.5)
+    run_pinn_literal("apts_pinn_literal_ws2", 2, 10, 29644)
+
+
 def run_kernel_level(name):
     """Direct calls of LSR1.update_memory / precompute / B and solve_tr_second_order on
     synthetic (s, y) pairs: y = A s for a fixed indefinite diagonal-plus-low-rank A."""
@@ -424,6 +555,10 @@ def run_samplers(name):
 
 
 def main():
+    if "--only-config5" in sys.argv:
+        torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+        run_config5_all()
+        return
     if "--only-samplers" in sys.argv:
         run_samplers("samplers")
         return
@@ -458,6 +593,7 @@ def main():
              dtype=torch.float64, port=29607)
     run_apts("apts_p_tr_so_ws2", "apts_p", 2, "tr", "tr", True, False, 3, 12, port=29608)
     run_pinn("apts_pinn_ws2", 2, 10, port=29609)
+    run_config5_all()
     run_tradam("tradam_inf", math.inf, 0.01, 20)
     run_tradam("tradam_l2", 2, 0.5, 20)
     run_samplers("samplers")
