@@ -67,12 +67,16 @@ struct FocOp {
     }
 };
 
-template <class WT>
+// BT: dtype of the reference's pre-allocated `_step_buffer` / coalesced all-reduce buffer, i.e. the
+// dtype the model had when the optimizer was CONSTRUCTED (apts_d.py:112,129-141, apts_p.py:108).  It
+// differs from WT when the Trainer converts the model afterwards (trainer.py:1203-1211): the step is
+// then rounded to BT and summed over the subdomains in BT.
+template <class WT, class BT>
 struct PackOp {
     static constexpr int NRED = 0;
     static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
-    WT* buf;
+    BT* buf;
     const WT* wl;
     const WT* w0;
     const void* loss0;
@@ -84,8 +88,8 @@ struct PackOp {
     __device__ void setup() {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             const double red = ld_scalar(loss0, lt) - ld_scalar(loss1, lt);
-            buf[n] = (WT)((lt == 0 ? (double)(float)red : red) * weight);
-            buf[n + 1] = (WT)evals;
+            buf[n] = (BT)((lt == 0 ? (double)(float)red : red) * weight);
+            buf[n + 1] = (BT)evals;
         }
     }
     __device__ bool active() const { return true; }
@@ -95,20 +99,20 @@ struct PackOp {
         ld_ro<V, WT>(wl, i, a);
         ld_ro<V, WT>(w0, i, b);
 #pragma unroll
-        for (int e = 0; e < V; ++e) a[e] -= b[e];
-        st_v<V, WT>(buf, i, a);
+        for (int e = 0; e < V; ++e) a[e] = rnd<WT>(a[e] - b[e]);
+        st_v<V, BT>(buf, i, a);
     }
     __device__ void finalize(const double*, ks::Scratch*, dd4ml_state*) {}
 };
 
-template <class WT>
+template <class WT, class BT>
 struct AptsTrialOp {
     static constexpr int NRED = 0;
     static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     WT* w;
     const WT* w0;
-    const WT* buf;
+    const void* buf;      // mode 0: the summed step (BT); mode 1: the merged parameters (WT)
     int mode;
     double scale, clampv;
     __device__ dd4ml_state* state() const { return nullptr; }
@@ -118,12 +122,14 @@ struct AptsTrialOp {
     __device__ __forceinline__ void body(int64_t i, double*) {
         double a[V], b[V];
         ld_ro<V, WT>(w0, i, a);
-        ld_ro<V, WT>(buf, i, b);
+        if (mode == 0) ld_ro<V, BT>(reinterpret_cast<const BT*>(buf), i, b);
+        else ld_ro<V, WT>(reinterpret_cast<const WT*>(buf), i, b);
+        const double cl = rnd<BT>(clampv);   // clamp_ on a BT tensor compares against the bound in BT
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             double s;
-            if (mode == 0) s = rnd<WT>(b[e] * scale);
-            else { s = rnd<WT>(b[e] - a[e]); s = fmin(fmax(s, -clampv), clampv); }
+            if (mode == 0) s = rnd<BT>(b[e] * scale);
+            else { s = rnd<BT>(rnd<WT>(b[e] - a[e])); s = fmin(fmax(s, -cl), cl); }
             a[e] += s;
         }
         st_v<V, WT>(w, i, a);
@@ -209,22 +215,24 @@ int dd4ml_apts_foc(double* state, double* ws, const void* w_loc, const void* w_g
 
 int dd4ml_apts_pack(void* buf, const void* w_loc, const void* w0, const void* loss0,
                     const void* loss1, int lt, double weight, double evals, int64_t n, int wt,
-                    void* stream) {
+                    int bt, void* stream) {
     if (!buf || !w_loc || !w0 || !loss0 || !loss1 || n < 0) return DD4ML_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = aligned16(buf) && aligned16(w_loc) && aligned16(w0);
-    if (wt == 0) { PackOp<float> op{(float*)buf, (const float*)w_loc, (const float*)w0, loss0, loss1, lt, weight, evals, n}; return launch(op, n, vec, nullptr, 4, s); }
-    if (wt == 1) { PackOp<double> op{(double*)buf, (const double*)w_loc, (const double*)w0, loss0, loss1, lt, weight, evals, n}; return launch(op, n, vec, nullptr, 4, s); }
+    if (wt == 0 && bt == 0) { PackOp<float, float> op{(float*)buf, (const float*)w_loc, (const float*)w0, loss0, loss1, lt, weight, evals, n}; return launch(op, n, vec, nullptr, 4, s); }
+    if (wt == 1 && bt == 1) { PackOp<double, double> op{(double*)buf, (const double*)w_loc, (const double*)w0, loss0, loss1, lt, weight, evals, n}; return launch(op, n, vec, nullptr, 4, s); }
+    if (wt == 1 && bt == 0) { PackOp<double, float> op{(float*)buf, (const double*)w_loc, (const double*)w0, loss0, loss1, lt, weight, evals, n}; return launch(op, n, vec, nullptr, 4, s); }
     return DD4ML_E_DTYPE;
 }
 
 int dd4ml_apts_trial(void* w, const void* w0, const void* buf, int mode, double scale,
-                     double clampv, int64_t n, int wt, void* stream) {
+                     double clampv, int64_t n, int wt, int bt, void* stream) {
     if (!w || !w0 || !buf || n < 0 || (mode != 0 && mode != 1)) return DD4ML_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = aligned16(w) && aligned16(w0) && aligned16(buf);
-    if (wt == 0) { AptsTrialOp<float> op{(float*)w, (const float*)w0, (const float*)buf, mode, scale, clampv}; return launch(op, n, vec, nullptr, 4, s); }
-    if (wt == 1) { AptsTrialOp<double> op{(double*)w, (const double*)w0, (const double*)buf, mode, scale, clampv}; return launch(op, n, vec, nullptr, 4, s); }
+    if (wt == 0 && bt == 0) { AptsTrialOp<float, float> op{(float*)w, (const float*)w0, buf, mode, scale, clampv}; return launch(op, n, vec, nullptr, 4, s); }
+    if (wt == 1 && bt == 1) { AptsTrialOp<double, double> op{(double*)w, (const double*)w0, buf, mode, scale, clampv}; return launch(op, n, vec, nullptr, 4, s); }
+    if (wt == 1 && bt == 0) { AptsTrialOp<double, float> op{(double*)w, (const double*)w0, buf, mode, scale, clampv}; return launch(op, n, vec, nullptr, 4, s); }
     return DD4ML_E_DTYPE;
 }
 

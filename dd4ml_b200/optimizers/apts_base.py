@@ -79,6 +79,10 @@ class APTS_Base(Optimizer):
         self.model = model
         self._gfs = get_flat(list(model.parameters()))       # bind BEFORE the global optimizer so it reuses it
         self.device = self._gfs.device
+        # dtype of the model at construction: the reference pre-allocates `_step_buffer` (and sizes its
+        # coalesced all-reduce buffer after it) here (apts_d.py:112, apts_p.py:108), so when the Trainer
+        # converts the model to float64 afterwards the step keeps being rounded to this dtype
+        self._ctor_dtype = self._gfs.dtype
         self.glob_opt = glob_opt(self.model.parameters(), **glob_opt_hparams)
         if isinstance(self.glob_opt, LSSR1_TR):
             self.glob_opt._elide_sync = True    # glob_closure_main all-reduces loss and gradient already
@@ -156,9 +160,14 @@ class APTS_Base(Optimizer):
         if self._bufs is None or self._bufs_version != ver:
             n, dev, wt = self._gfs.n, self.device, self._gfs.dtype
             z = lambda k=n, d=wt: torch.zeros(k, dtype=d, device=dev)  # noqa: E731
-            self._bufs = {"w0": z(), "g0": z(), "gl0": z(), "resid": z(), "comm": z(n + 2)}
+            self._bufs = {"w0": z(), "g0": z(), "gl0": z(), "resid": z(), "comm": z(n + 2, self._comm_dtype())}
             self._bufs_version = ver
         return self._bufs
+
+    def _comm_dtype(self):
+        """APTS_D sums the subdomain steps in the dtype of the reference's coalesced buffer
+        (= construction dtype, apts_d.py:129-141); APTS_P merges full parameters (model dtype)."""
+        return self._gfs.dtype
 
     def _update_param_group(self):                       # apts_base.py:167-170
         for key in self.param_groups[0].keys():
@@ -303,7 +312,7 @@ class APTS_Base(Optimizer):
                                closure=self.glob_closure_main if closure is None else closure)
 
     # ------------------------------------------------------------------ control step
-    def _control(self, buf, mode, scale, clampv, f0, pred_ptr, pred_dt, aux_ptr):
+    def _control(self, buf, mode, scale, clampv, f0, pred_ptr, pred_dt, aux_ptr, bt=None):
         """apts_base.py:432-501 with `pred` supplied (APTS_D / APTS_P).  `buf` holds the combined
         step (mode 0) or the merged parameters (mode 1).  Returns (loss, grad, delta)."""
         b = self._buffers()
@@ -312,7 +321,7 @@ class APTS_Base(Optimizer):
         st = _lib.stream()
         self._push_ctl()
         lib.apts_trial(_lib.ptr(self._gfs.data), _lib.ptr(b["w0"]), _lib.ptr(buf), mode, float(scale),
-                       float(clampv), n, wt, st)
+                       float(clampv), n, wt, _lib.dt(self._ctor_dtype if bt is None else bt), st)
         trial = as_device_scalar(self.glob_closure_main(compute_grad=True), self.device)
         f0 = as_device_scalar(f0, self.device)
         if trial.dtype != f0.dtype:
@@ -359,8 +368,11 @@ class APTS_Base(Optimizer):
         b["w0"].copy_(self.init_glob_flat)
         b["g0"].copy_(self.init_glob_grad)
         pred_t = as_device_scalar(pred, self.device)
-        out, g, delta, _, _ = self._control(step.contiguous(), 0, 1.0, 0.0, self.init_glob_loss,
-                                            _lib.ptr(pred_t), _lib.dt(pred_t.dtype), None)
+        step = step.contiguous()
+        if step.dtype not in (torch.float32, self._gfs.dtype):
+            step = step.to(self._gfs.dtype)
+        out, g, delta, _, _ = self._control(step, 0, 1.0, 0.0, self.init_glob_loss,
+                                            _lib.ptr(pred_t), _lib.dt(pred_t.dtype), None, bt=step.dtype)
         if delta is None:               # device-control mode: the public form reports delta to the host
             delta, _, _ = self._read_control()
         return out, g, delta

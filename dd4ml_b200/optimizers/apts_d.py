@@ -62,6 +62,9 @@ class APTS_D(APTS_Base):
         from ..graphs import GraphedEval
         self._loc_eval = GraphedEval(self.loc_model, self.criterion, self._lfs)
 
+    def _comm_dtype(self):
+        return self._ctor_dtype
+
     # ------------------------------------------------------------------ apts_base.py:228-243
     @torch.no_grad()
     def sync_glob_to_loc(self):
@@ -143,7 +146,8 @@ class APTS_D(APTS_Base):
         comm = b["comm"]
         lib.apts_pack(_lib.ptr(comm), _lib.ptr(self._lfs.data), _lib.ptr(b["w0"]), _lib.ptr(self.init_loc_loss),
                       _lib.ptr(loc_loss), _lib.dt(self.init_loc_loss.dtype),
-                      float(weight) if self.nr_models > 1 else 1.0, float(self.loc_grad_evals), n, wt, st)
+                      float(weight) if self.nr_models > 1 else 1.0, float(self.loc_grad_evals), n, wt,
+                      _lib.dt(comm.dtype), st)
         scale = 1.0
         if self._distributed:
             dist.all_reduce(comm, op=dist.ReduceOp.SUM)             # additive Schwarz (apts_d.py:144)
@@ -152,7 +156,7 @@ class APTS_D(APTS_Base):
         use(glob_io, on_glob)
         es = comm.element_size()
         loss, grad, delta, evals_sum, gn = self._control(
-            comm, 0, scale, 0.0, self.init_glob_loss, comm.data_ptr() + n * es, wt,
+            comm, 0, scale, 0.0, self.init_glob_loss, comm.data_ptr() + n * es, _lib.dt(comm.dtype),
             comm.data_ptr() + (n + 1) * es)
         if self._device_control:
             self._link(self.glob_opt._ds, self._ctl)                  # glob_opt.delta <- control delta

@@ -53,6 +53,9 @@ class APTS_P(APTS_Base):
         self._lfs = FlatSlice(fb, 0, fb.n)
         owned = [lps[i] for i in owned_idx]
         self.loc_opt = loc_opt(params=owned, **loc_opt_hparams)
+        # the reference passes flat_grads_fn / flat_params_fn hooks to this optimizer (apts_p.py:76-81):
+        # its vectors bypass the construction-dtype flat buffers of TR / LSSR1_TR
+        self.loc_opt._ref_hooks = True
         self.loc_closure = self.non_foc_loc_closure
         self._layout()
         self.sqrt_n_global = math.sqrt(self.n_global)

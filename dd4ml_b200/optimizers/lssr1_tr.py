@@ -78,6 +78,12 @@ class LSSR1_TR(Optimizer):
         self._fs = get_flat(self.ps)
         self._fs_version = self._fs.version
         device, dtype = self._fs.device, self._fs.dtype           # lssr1_tr.py:99-106
+        # The reference allocates flat_wk / flat_gk in this dtype and routes the parameters and every
+        # evaluated gradient through them (lssr1_tr.py:119-142, 205-229) unless flat hooks are given
+        # (APTS_P's local optimizer).  If the model is converted afterwards (Trainer's .double(),
+        # trainer.py:1203-1211) both keep being rounded to the construction dtype; reproduced below.
+        self._ctor_dtype = dtype
+        self._ref_hooks = False          # set by APTS_P for its local optimizer
         self.obs = None
         self.hess = LSR1(gamma=self._gamma0, memory_length=self.mem_length, device=device, dtype=dtype,
                          tol=self.tol)
@@ -172,6 +178,9 @@ class LSSR1_TR(Optimizer):
         dist.broadcast(grad, src=0)
         return buf.to(loss_t.dtype)
 
+    def _emulate_ctor_dtype(self) -> bool:
+        return (not self._ref_hooks) and self._fs.dtype != self._ctor_dtype
+
     # ------------------------------------------------------------------ evaluations
     def _evaluate(self, alpha, closure):
         """lssr1_tr.py:247-278: move to w_k + alpha p, evaluate, directional derivative."""
@@ -194,6 +203,8 @@ class LSSR1_TR(Optimizer):
         loss = closure(compute_grad=True)
         self.n_evals += 1
         G = self._fs.flat_grad()
+        if self._emulate_ctor_dtype():
+            G = G.to(self._ctor_dtype)                 # _flatten_grads through the flat_gk buffer
         loss_t = self._sync_eval(as_device_scalar(loss, self._fs.device), G)
         if loss_t is not loss and self.sync and self.world_size > 1 and not self._elide_sync:
             loss = loss_t
@@ -299,13 +310,20 @@ class LSSR1_TR(Optimizer):
             self._pushed_delta = (self.delta, self.min_delta, self.max_delta)
         st = _lib.stream()
         vtc, wtc, htc = _lib.dt(g.dtype), _lib.dt(self._fs.dtype), _lib.dt(h.dtype)
-        lib.lssr1_begin(ds.sp, ds.wp, _lib.ptr(self._fs.data), _lib.ptr(b["old_w"]), _lib.ptr(g),
+        emul = self._emulate_ctor_dtype()
+        w_in = self._fs.data
+        if emul:                                     # wk = _flatten_params() through the flat_wk buffer
+            w_in = b.get("w_round")
+            if w_in is None:
+                w_in = b["w_round"] = torch.empty_like(self._fs.data)
+            w_in.copy_(self._fs.data.to(self._ctor_dtype))
+        lib.lssr1_begin(ds.sp, ds.wp, _lib.ptr(w_in), _lib.ptr(b["old_w"]), _lib.ptr(g),
                         _lib.ptr(b["prev_g"]), 1 if self._has_prev else 0, h.S_ptr, h.Y_ptr,
                         _lib.ptr(loss_t), _lib.dt(loss_t.dtype), n, h.ld, vtc, htc, wtc, self.mem_length, *rad, st)
         # The first trial point of the line search is w_k + 1.0 p (alpha_max / 2, lssr1_tr.py:397): when
         # it is evaluated speculatively, the direction kernel applies it on the way (w += p) instead
         # of a separate trial launch.  (begin has just stored old_w = w_k, so w + p == old_w + 1.0 p.)
-        fuse_first = self.speculative_first_eval and 0.5 * self.alpha_max == 1.0
+        fuse_first = self.speculative_first_eval and 0.5 * self.alpha_max == 1.0 and not emul
         lib.tr_apply(ds.sp, ds.wp, _lib.ptr(g), h.S_ptr, h.Y_ptr, _lib.ptr(b["p"]),
                      _lib.ptr(self._fs.data) if fuse_first else None, n, h.ld, vtc, htc, wtc, self.mem_length, st)
         self._applied_alpha = 1.0 if fuse_first else 0.0

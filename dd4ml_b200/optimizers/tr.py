@@ -84,6 +84,7 @@ class TR(Optimizer):
             raise _lib.DD4MLError("dd4ml_b200 TR supports norm_type 2 and inf")
         self._flat_grads_fn = flat_grads_fn
         self._flat_params_fn = flat_params_fn
+        self._ref_hooks = flat_grads_fn is not None      # also set by APTS_P for its local optimizer
         # sync-free mode (north star: ratio test and radius update on the device, no host sync per
         # inner iteration): set by the APTS classes, or TR(..., device_control=True)
         self.device_control = bool(kwargs.pop("device_control", False))
@@ -160,6 +161,19 @@ class TR(Optimizer):
             g = self._flat_grads_fn()
             return g if g.dtype == vt else g.to(vt)
         G = self._fs.flat_grad()
+        if G.dtype == torch.float64 and not self._ref_hooks:
+            # tr.py:69,88-104: without flat hooks every gradient passes through the float32 `_grad_buf`
+            # (SURVEY Q4), also in float64 runs -- keep the rounding, whatever dtype carries the values
+            b = self._buffers(vt)
+            c32 = b.get("g_f32")
+            if c32 is None:
+                c32 = b["g_f32"] = torch.empty(self._fs.n, dtype=torch.float32, device=self._fs.device)
+            c32.copy_(G)
+            if vt == torch.float32:
+                return c32
+            c = b.setdefault("g_cast", torch.empty_like(b["step"]))
+            c.copy_(c32)
+            return c
         if G.dtype == vt:
             return G
         b = self._buffers(vt)

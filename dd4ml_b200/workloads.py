@@ -112,3 +112,143 @@ def allen_cahn_points(n_interior=1000, low=0.0, high=1.0):
     mask = torch.cat([torch.ones(2, 1), torch.zeros(n_interior, 1)], 0)
     idx = torch.argsort(data[:, 0])
     return data[idx], mask[idx]
+
+
+# ---------------------------------------------------------------------------------------------------
+# The other BASELINE models at their native sizes (forward/backward = plain PyTorch, untouched)
+class DeepONet(nn.Module):
+    """Branch 50 -> 64 -> 64, trunk 1 -> 64 -> 64, ReLU after every layer, y = sum(b * t)
+    (reference models/deeponet/deeponet.py:9-42): n = 11 712 parameters, 8 tensors."""
+
+    def __init__(self, sensors=50, width=(64, 64), trunk_in=1):
+        super().__init__()
+
+        def mlp(i):
+            mods = []
+            for h in width:
+                mods += [nn.Linear(i, h), nn.ReLU()]
+                i = h
+            return nn.Sequential(*mods)
+        self.branch_net, self.trunk_net = mlp(sensors), mlp(trunk_in)
+
+    def forward(self, inputs):
+        branch, trunk = inputs
+        return (self.branch_net(branch) * self.trunk_net(trunk)).sum(dim=1, keepdim=True)
+
+
+def deeponet_sine_batch(n_items=1000, seed=42, n_samples=1000, n_sensors=50, n_trunk=100):
+    """First `n_items` items of the reference's SineOperatorDataset (datasets/deeponet_sine.py:9-45):
+    functions a -> sin(a x), a ~ U(0,1), sampled at 50 sensors / 100 trunk points on [0, 2 pi];
+    returns (branch [B,50], trunk [B,1], y [B,1]) with float targets."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    hi = 2 * math.pi
+    sensors, trunk = torch.linspace(0.0, hi, n_sensors), torch.linspace(0.0, hi, n_trunk)
+    a = torch.rand(n_samples, generator=g)
+    idx = torch.arange(n_items)
+    s_idx, t_idx = idx // n_trunk, idx % n_trunk
+    branch = torch.sin(a[s_idx].unsqueeze(1) * sensors)
+    x = trunk[t_idx].unsqueeze(1)
+    return branch, x, torch.sin(a[s_idx].unsqueeze(1) * x)
+
+
+class SimpleCNN(nn.Module):
+    """3 x (conv3x3 -> BatchNorm -> ReLU -> maxpool2) with 32/64/128 channels, fc 2048 -> 256 -> 10,
+    Dropout(0.5) (reference models/cnn/simple_cnn.py:81-110) on CIFAR-10-shape input:
+    n = 620 810 parameters, 16 tensors."""
+
+    def __init__(self, in_ch=3, hw=32, classes=10, p_drop=0.5):
+        super().__init__()
+        chans = [in_ch, 32, 64, 128]
+        self.convs = nn.ModuleList([nn.Conv2d(a, b, 3, padding=1) for a, b in zip(chans[:-1], chans[1:])])
+        self.norms = nn.ModuleList([nn.BatchNorm2d(c) for c in chans[1:]])
+        self.fc1 = nn.Linear(chans[-1] * (hw // 8) ** 2, 256)
+        self.drop = nn.Dropout(p_drop)
+        self.fc2 = nn.Linear(256, classes)
+
+    def forward(self, x):
+        for conv, bn in zip(self.convs, self.norms):
+            x = F.max_pool2d(F.relu(bn(conv(x))), 2)
+        x = F.relu(self.fc1(x.flatten(1)))
+        return self.fc2(self.drop(x))
+
+    def parameters_in_reference_order(self):
+        """conv1, bn1, conv2, bn2, conv3, bn3, fc1, fc2 -- the registration order of the reference
+        class (its `parameters()` order), for loading a flat reference vector."""
+        out = []
+        for conv, bn in zip(self.convs, self.norms):
+            out += list(conv.parameters()) + list(bn.parameters())
+        return out + list(self.fc1.parameters()) + list(self.fc2.parameters())
+
+
+def cifar_shape_batch(n_samples, seed, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n_samples, 3, 32, 32, generator=g)
+    y = torch.randint(0, 10, (n_samples,), generator=g)
+    return (x.pin_memory(), y.pin_memory()) if pin else (x, y)
+
+
+class _GPTBlock(nn.Module):
+    def __init__(self, d, heads, block, p):
+        super().__init__()
+        self.ln_1, self.ln_2 = nn.LayerNorm(d), nn.LayerNorm(d)
+        self.c_attn, self.c_proj = nn.Linear(d, 3 * d), nn.Linear(d, d)
+        self.c_fc, self.c_proj2 = nn.Linear(d, 4 * d), nn.Linear(4 * d, d)
+        self.heads, self.p = heads, p
+        self.register_buffer("mask", torch.tril(torch.ones(block, block)).view(1, 1, block, block))
+
+    def forward(self, x):
+        B, T, C = x.shape
+        q, k, v = self.c_attn(self.ln_1(x)).split(C, dim=2)
+        sh = lambda t: t.view(B, T, self.heads, C // self.heads).transpose(1, 2)  # noqa: E731
+        q, k, v = sh(q), sh(k), sh(v)
+        att = (q @ k.transpose(-2, -1)) * (1.0 / (k.size(-1) ** 0.5))
+        att = att.masked_fill(self.mask[:, :, :T, :T] == 0, float("-inf"))
+        att = F.dropout(F.softmax(att, dim=-1), self.p, self.training)
+        y = (att @ v).transpose(1, 2).contiguous().view(B, T, C)
+        x = x + F.dropout(self.c_proj(y), self.p, self.training)
+        h = self.c_fc(self.ln_2(x))
+        h = 0.5 * h * (1.0 + torch.tanh(0.7978845608028654 * (h + 0.044715 * torch.pow(h, 3.0))))
+        return x + F.dropout(self.c_proj2(h), self.p, self.training)
+
+
+class MiniGPT(nn.Module):
+    """minGPT `gpt-mini`: 6 layers, 6 heads, width 192, vocab 65, block 128, dropout 0.1
+    (reference models/gpt/base_gpt.py:181, models/gpt/nanogpt/model.py:31-92): n = 2 719 104
+    parameters, 77 tensors (wte, wpe, 6 x 12, ln_f x 2, lm_head without bias)."""
+
+    def __init__(self, vocab=65, block=128, layers=6, heads=6, d=192, p_drop=0.1):
+        super().__init__()
+        self.wte, self.wpe = nn.Embedding(vocab, d), nn.Embedding(block, d)
+        self.h = nn.ModuleList([_GPTBlock(d, heads, block, p_drop) for _ in range(layers)])
+        self.ln_f = nn.LayerNorm(d)
+        self.lm_head = nn.Linear(d, vocab, bias=False)
+        self.p = p_drop
+        for m in self.modules():                      # GPT-2 initialisation (model.py:83-92, 49-54)
+            if isinstance(m, (nn.Linear, nn.Embedding)):
+                nn.init.normal_(m.weight, mean=0.0, std=0.02)
+                if isinstance(m, nn.Linear) and m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        for blk in self.h:
+            nn.init.normal_(blk.c_proj.weight, mean=0.0, std=0.02 / (2 * layers) ** 0.5)
+            nn.init.normal_(blk.c_proj2.weight, mean=0.0, std=0.02 / (2 * layers) ** 0.5)
+
+    def forward(self, idx):
+        T = idx.size(1)
+        pos = torch.arange(T, device=idx.device).unsqueeze(0)
+        x = F.dropout(self.wte(idx) + self.wpe(pos), self.p, self.training)
+        for blk in self.h:
+            x = blk(x)
+        return self.lm_head(self.ln_f(x))
+
+
+def token_cross_entropy(logits, targets):
+    """utility/ml_utils.py:33-36 (`cross_entropy_transformers`)."""
+    return F.cross_entropy(logits.view(-1, logits.size(-1)), targets.view(-1), ignore_index=-1)
+
+
+def token_batch(batch, seed, block=128, vocab=65, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(0, vocab, (batch, block), generator=g)
+    y = torch.randint(0, vocab, (batch, block), generator=g)
+    return (x.pin_memory(), y.pin_memory()) if pin else (x, y)

@@ -101,6 +101,11 @@ int dd4ml_lssr1_eval(double* state, double* ws, const void* g, const void* p, vo
  *           (apts_d.py:195-196,139-141; apts_base.py:411-416) -- the all-reduce payload.
  * trial:    mode 0: w = w0 + buf*scale (apts_base.py:445, apts_d.py:149-150);
  *           mode 1: w = w0 + clamp(buf - w0, -clampv, clampv) (apts_p.py:221-224).
+ *           `bt` = dtype of the reference's pre-allocated `_step_buffer` / coalesced buffer
+ *           (apts_d.py:112,129-141, apts_p.py:108), i.e. the dtype the model had when the optimizer
+ *           was constructed: pack writes buf[0:n+2] in bt, trial mode 0 reads the step in bt and
+ *           mode 1 (buf = merged parameters, dtype wt) rounds the step and the clamp bound to bt.
+ *           bt == wt unless the model was converted after construction (trainer.py:1203-1211).
  * control:  APTS_Base.control_step decision (apts_base.py:483-501): accepted: g0 <- G
  *           (trial gradient), loss_out <- f_trial; rejected: w <- w0, loss_out <- f0;
  *           radius update on `state`; `aux` (nullable, dtype pt) is copied into state.aux so the
@@ -112,9 +117,9 @@ int dd4ml_apts_foc(double* state, double* ws, const void* w_loc, const void* w_g
                    int64_t n, int vt, int wt, void* stream);
 int dd4ml_apts_pack(void* buf, const void* w_loc, const void* w0, const void* loss0,
                     const void* loss1, int lt, double weight, double evals, int64_t n, int wt,
-                    void* stream);
+                    int bt, void* stream);
 int dd4ml_apts_trial(void* w, const void* w0, const void* buf, int mode, double scale,
-                     double clampv, int64_t n, int wt, void* stream);
+                     double clampv, int64_t n, int wt, int bt, void* stream);
 int dd4ml_apts_control(double* state, double* ws, const void* f0, const void* ftrial, int lt,
                        const void* pred, int pt, void* w, const void* w0, void* g0, const void* G,
                        void* loss_out, const void* aux, int64_t n, int vt, int wt, void* stream);

@@ -209,13 +209,23 @@ def test_apts_vector_kernels_match_torch():
             assert float(out) == 1.25                      # identical models: no term
             comm = torch.empty(n + 2, dtype=dtype, device=DEV)
             l0 = torch.tensor(2.0, device=DEV); l1 = torch.tensor(1.5, device=DEV)
-            lib.apts_pack(comm.data_ptr(), wl.data_ptr(), wg.data_ptr(), l0.data_ptr(), l1.data_ptr(), 0, 0.5, 7.0, n, wt, st)
+            lib.apts_pack(comm.data_ptr(), wl.data_ptr(), wg.data_ptr(), l0.data_ptr(), l1.data_ptr(), 0, 0.5, 7.0, n, wt, wt, st)
             assert torch.equal(comm[:n], wl - wg) and float(comm[n]) == 0.25 and float(comm[n + 1]) == 7.0
             w = torch.empty_like(wg)
-            lib.apts_trial(w.data_ptr(), wg.data_ptr(), comm.data_ptr(), 0, 0.5, 0.0, n, wt, st)
+            lib.apts_trial(w.data_ptr(), wg.data_ptr(), comm.data_ptr(), 0, 0.5, 0.0, n, wt, wt, st)
             assert rel_err(w.cpu(), (wg + comm[:n] * 0.5).cpu()) < 1e-7
-            lib.apts_trial(w.data_ptr(), wg.data_ptr(), wl.data_ptr(), 1, 1.0, 0.3, n, wt, st)
+            lib.apts_trial(w.data_ptr(), wg.data_ptr(), wl.data_ptr(), 1, 1.0, 0.3, n, wt, wt, st)
             assert rel_err(w.cpu(), (wg + (wl - wg).clamp(-0.3, 0.3)).cpu()) < 1e-7
+            if dtype == torch.float64:
+                # model converted to float64 AFTER construction (trainer.py:1203-1211): the reference's
+                # float32 `_step_buffer` / coalesced buffer round the step (apts_d.py:112,196, apts_p.py:108,221)
+                c32 = torch.empty(n + 2, dtype=torch.float32, device=DEV)
+                lib.apts_pack(c32.data_ptr(), wl.data_ptr(), wg.data_ptr(), l0.data_ptr(), l1.data_ptr(), 0, 0.5, 7.0, n, 1, 0, st)
+                assert torch.equal(c32[:n], (wl - wg).float()) and float(c32[n]) == 0.25 and float(c32[n + 1]) == 7.0
+                lib.apts_trial(w.data_ptr(), wg.data_ptr(), c32.data_ptr(), 0, 0.5, 0.0, n, 1, 0, st)
+                assert torch.equal(w, wg + (c32[:n] * 0.5).double())
+                lib.apts_trial(w.data_ptr(), wg.data_ptr(), wl.data_ptr(), 1, 1.0, 0.3, n, 1, 0, st)
+                assert torch.equal(w, wg + (wl - wg).float().clamp_(-0.3, 0.3).double())
             # control: accept and reject
             for f1, expect in ((1.0, True), (1.99, False)):
                 ds.set(delta=0.1, min_delta=0.01, max_delta=1.0, nu_dec=0.25, nu_inc=0.75, inc_factor=1.2,
