@@ -28,6 +28,18 @@ class _Entry:
 
 
 class GraphedEval:
+    PROF = None       # bench.py: list of (start_event, end_event) per evaluation when profiling
+
+    def __call__(self, inputs, labels):
+        if GraphedEval.PROF is None:
+            return self._call(inputs, labels)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = self._call(inputs, labels)
+        e1.record()
+        GraphedEval.PROF.append((e0, e1))
+        return out
+
     def __init__(self, model, criterion, flat, long_labels=True, warmup=3):
         self.model, self.criterion, self.flat = model, criterion, flat
         self.long_labels = long_labels
@@ -77,7 +89,7 @@ class GraphedEval:
         self.captures += 1
         return e
 
-    def __call__(self, inputs, labels):
+    def _call(self, inputs, labels):
         if (not ENABLED or not torch.is_tensor(inputs) or not torch.is_tensor(labels) or inputs.requires_grad
                 or not inputs.is_cuda):
             return self._eval(inputs, labels)

@@ -30,6 +30,21 @@ from .lssr1_tr import LSSR1_TR
 from .tr import TR, as_device_scalar
 
 
+COMM_PROF = None      # bench.py: list of (start_event, end_event, numel) per collective when profiling
+
+
+def all_reduce(t, op):
+    """Every collective of the APTS path goes through here (NCCL on the current stream)."""
+    if COMM_PROF is None:
+        dist.all_reduce(t, op=op)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dist.all_reduce(t, op=op)
+    e1.record()
+    COMM_PROF.append((e0, e1, t.numel()))
+
+
 class APTS_Base(Optimizer):
     __name__ = "APTS_Base"
 
@@ -274,9 +289,9 @@ class APTS_Base(Optimizer):
 
     def _allreduce_mean(self, t):
         if dist.get_backend() == "nccl":
-            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+            all_reduce(t, dist.ReduceOp.AVG)
         else:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            all_reduce(t, dist.ReduceOp.SUM)
             t.div_(self.nr_models)
 
     # ------------------------------------------------------------------ inner loops

@@ -21,6 +21,7 @@ import torch.distributed as dist
 from .. import _lib
 from ..flat import get_flat
 from ..utility.apts_utils import clone_model
+from . import apts_base
 from .apts_base import APTS_Base
 from .tr import as_device_scalar
 
@@ -150,7 +151,7 @@ class APTS_D(APTS_Base):
                       _lib.dt(comm.dtype), st)
         scale = 1.0
         if self._distributed:
-            dist.all_reduce(comm, op=dist.ReduceOp.SUM)             # additive Schwarz (apts_d.py:144)
+            apts_base.all_reduce(comm, dist.ReduceOp.SUM)             # additive Schwarz (apts_d.py:144)
             if self.norm_type == math.inf:
                 scale = 1.0 / self.nr_models
         use(glob_io, on_glob)

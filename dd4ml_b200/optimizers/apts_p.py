@@ -21,6 +21,7 @@ import torch.distributed as dist
 from .. import _lib
 from ..flat import FlatBuffer, FlatSlice
 from ..utility.apts_utils import clone_model, mark_trainable
+from . import apts_base
 from .apts_base import APTS_Base
 from .tr import as_device_scalar
 
@@ -141,7 +142,7 @@ class APTS_P(APTS_Base):
         if evals is not None:
             comm[self.n_global + 1:self.n_global + 2].fill_(float(evals))   # (fill_, not item assignment: no host->device copy)
         if self._distributed:
-            dist.all_reduce(comm, op=dist.ReduceOp.SUM)
+            apts_base.all_reduce(comm, dist.ReduceOp.SUM)
         return comm
 
     # ------------------------------------------------------------------ apts_p.py:167-180

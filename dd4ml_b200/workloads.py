@@ -252,3 +252,13 @@ def token_batch(batch, seed, block=128, vocab=65, pin=False):
     x = torch.randint(0, vocab, (batch, block), generator=g)
     y = torch.randint(0, vocab, (batch, block), generator=g)
     return (x.pin_memory(), y.pin_memory()) if pin else (x, y)
+
+
+def teacher_labels(X, seed=7, hidden=64, classes=10):
+    """Labels a fixed random teacher MLP assigns to X (learnable targets: with uniform random labels
+    the N >= 2 APTS_D runs stall at ln 10 after one outer iteration, which makes per-N work unequal)."""
+    g = torch.Generator().manual_seed(seed)
+    d = X[0].numel()
+    w1 = torch.randn(d, hidden, generator=g) / d ** 0.5
+    w2 = torch.randn(hidden, classes, generator=g) / hidden ** 0.5
+    return (torch.tanh(X.reshape(X.size(0), -1).float() @ w1) @ w2).argmax(dim=1)

@@ -80,8 +80,9 @@ class LSR1Memory:
         # layout the reference hands to MKL (lsr1.py:112-120,158-160), so that the GEMM
         # rounding is reproduced as well.
         n = self.S[0].shape[0]
-        Sm = torch.zeros(n, self.m, dtype=self.dtype)
-        Ym = torch.zeros(n, self.m, dtype=self.dtype)
+        dev = self.S[0].device                     # (cpu everywhere except bench.py --impl aten)
+        Sm = torch.zeros(n, self.m, dtype=self.dtype, device=dev)
+        Ym = torch.zeros(n, self.m, dtype=self.dtype, device=dev)
         for j in range(k):
             Sm[:, j] = self.S[j]
             Ym[:, j] = self.Y[j]
@@ -90,5 +91,5 @@ class LSR1Memory:
         SY = S.t() @ Y
         Minv = (torch.diag(torch.diag(SY)) + torch.tril(SY, -1)
                 + torch.tril(SY, -1).t() - self.gamma * (S.t() @ S))
-        Minv = Minv + (self.tol * torch.norm(Minv, p="fro")) * torch.eye(k, dtype=self.dtype)
+        Minv = Minv + (self.tol * torch.norm(Minv, p="fro")) * torch.eye(k, dtype=self.dtype, device=dev)
         self.Minv = Minv

@@ -53,7 +53,7 @@ def _newton(x0, Lam, a, delta, tol=OBS_TOL, max_iter=200):
 def canonical_eigvec_signs(U: torch.Tensor) -> torch.Tensor:
     """Flip every column so its largest-|.| entry (lowest index on ties) is > 0."""
     idx = U.abs().argmax(dim=0)
-    sgn = torch.sign(U[idx, torch.arange(U.shape[1])])
+    sgn = torch.sign(U[idx, torch.arange(U.shape[1], device=U.device)])
     sgn[sgn == 0] = 1
     return U * sgn
 
@@ -84,7 +84,7 @@ def obs_solve(g, delta, gamma, Psi, Minv, *, eig_sign="lapack", info=None, tol=O
     if eig_sign == "canonical":
         U = canonical_eigvec_signs(U)
     k = D.shape[0]
-    Lam = torch.cat((D + gamma, gamma.view(1)))
+    Lam = torch.cat((D + gamma, gamma.view(1).to(D.device)))
     Lam[Lam.abs() < tol] = 0                                   # :79
     lam_min = torch.min(Lam[0], gamma)                         # :80
     RinvU = torch.linalg.solve(R, U)
@@ -104,7 +104,7 @@ def obs_solve(g, delta, gamma, Psi, Minv, *, eig_sign="lapack", info=None, tol=O
         return smw(gamma)
     if lam_min <= 0 and _phi_bar_f(-lam_min, Lam, a, delta, tol) >= 0:   # :100 case B (hard case)
         sig = -lam_min
-        v = torch.zeros(k + 1, dtype=a.dtype)
+        v = torch.zeros(k + 1, dtype=a.dtype, device=a.device)
         nz = (Lam + sig).abs() > tol
         v[nz] = a[nz] / (Lam[nz] + sig)
         P_par = Psi @ RinvU

@@ -559,6 +559,11 @@ def main():
         torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
         run_config5_all()
         return
+    if "--only-ws8" in sys.argv:
+        torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+        run_apts("apts_d_tr_fo_ws8", "apts_d", 8, "tr", "tr", False, False, 3, 8, port=29651)
+        run_apts("apts_d_lssr1_fo_ws8", "apts_d", 8, "lssr1_tr", "lssr1_tr", False, False, 3, 8, port=29652)
+        return
     if "--only-samplers" in sys.argv:
         run_samplers("samplers")
         return
@@ -593,6 +598,8 @@ def main():
              dtype=torch.float64, port=29607)
     run_apts("apts_p_tr_so_ws2", "apts_p", 2, "tr", "tr", True, False, 3, 12, port=29608)
     run_pinn("apts_pinn_ws2", 2, 10, port=29609)
+    run_apts("apts_d_tr_fo_ws8", "apts_d", 8, "tr", "tr", False, False, 3, 8, port=29651)
+    run_apts("apts_d_lssr1_fo_ws8", "apts_d", 8, "lssr1_tr", "lssr1_tr", False, False, 3, 8, port=29652)
     run_config5_all()
     run_tradam("tradam_inf", math.inf, 0.01, 20)
     run_tradam("tradam_l2", 2, 0.5, 20)

@@ -1,0 +1,140 @@
+"""Multi-rank parity leg of `bench.py --gpus N` (N >= 2): before anything is timed, the N ranks of the
+bench job run committed goldens of the UNMODIFIED reference (tests/golden/*_ws{N}.npz, produced by
+N gloo ranks of dd4ml.optimizers.apts_d / apts_p) for their recorded number of outer iterations and
+compare losses, radii and gradient-evaluation counts.  The driver's GPU test tier has one GPU, so this
+is where N-rank NCCL results are checked under the driver's own launch
+(reference: optimizers/apts_d.py:114-210, apts_p.py:115-245)."""
+from __future__ import annotations
+
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CASES = {
+    2: [("apts_d_tr_fo_ws2", "apts_d", 1e-3), ("apts_p_tr_fo_ws2", "apts_p", 1e-3),
+        ("config5_apts_p_tr_small_ws2", "config5", 1e-5)],
+    4: [("apts_d_lssr1_fo_ws4", "apts_d", 1e-3)],
+    8: [("apts_d_tr_fo_ws8", "apts_d", 1e-3), ("apts_d_lssr1_fo_ws8", "apts_d", 1e-3)],
+}
+
+
+class _Cfg:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _cfg(**kw):
+    base = dict(delta=0.1, min_delta=0.01, max_delta=1.0, norm_type=2, glob_second_order=False, glob_dogleg=False,
+                loc_second_order=False, loc_dogleg=False, mem_length=3, max_wolfe_iters=5, max_zoom_iters=5,
+                tol=1e-6, paper_tr_update=False)
+    base.update(kw)
+    return _Cfg(**base)
+
+
+def _patch_ownership(g, rank):
+    import dd4ml_b200.optimizers.apts_p as ap
+    owned = set(int(i) for i in g[f"owned_tensors_rank{rank}"])     # the reference's ownership draw
+
+    def mark(m):
+        for i, p in enumerate(m.parameters()):
+            p.requires_grad = i in owned
+        m._trainable_indices = sorted(owned)
+        return m
+    orig, ap.mark_trainable = ap.mark_trainable, mark
+    return lambda: setattr(ap, "mark_trainable", orig)
+
+
+def _run_case(name, kind, rank, ws, dev):
+    from _helpers import FFNN, load_golden, set_flat
+    from dd4ml_b200 import APTS_D, APTS_P
+    g = load_golden(name)
+    assert int(g["world_size"]) == ws
+    if kind == "config5":
+        from dd4ml_b200.workloads import AllenCahnLoss, PINNNet
+        model = PINNNet()
+        set_flat(model, torch.from_numpy(g["w0_f32"]))
+        model = model.to(dev)
+        crit = AllenCahnLoss()
+        c = _cfg(delta=float(g["delta0"]), min_delta=float(g["min_delta"]), max_delta=float(g["max_delta"]),
+                 norm_type=math.inf, mem_length=5, paper_tr_update=bool(g["paper_tr_update"]))
+        c.glob_opt, c.loc_opt = str(g["glob"]), str(g["loc"])
+        c = APTS_P.setup_APTS_hparams(c)
+        undo = _patch_ownership(g, rank)
+        opt = APTS_P(model.parameters(), model=model, criterion=crit, device=dev, nr_models=ws, glob_opt=c.glob_opt,
+                     glob_opt_hparams=c.glob_opt_hparams, loc_opt=c.loc_opt, loc_opt_hparams=c.loc_opt_hparams,
+                     glob_pass=True, norm_type=math.inf, max_loc_iters=3, max_glob_iters=1, tol=1e-6, **c.apts_params)
+        undo()
+        model = model.double()                                       # trainer.py:1203-1211
+        opt.loc_model = opt.loc_model.double()
+        x, y = torch.from_numpy(g["x"]).to(dev), torch.from_numpy(g["y"]).to(dev)
+        x.requires_grad_(True)
+        crit.current_x = x
+        step = lambda: opt.step(inputs=x, labels=y)  # noqa: E731
+    else:
+        model = FFNN(36, [12, 12], 10)
+        set_flat(model, torch.from_numpy(g["w0"]))
+        model = model.to(dev)
+        X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+        if kind == "apts_d":
+            per = X.shape[0] // ws
+            Xr, Yr = X[rank * per:(rank + 1) * per].to(dev), Y[rank * per:(rank + 1) * per].to(dev)
+            c = _cfg()
+            cls, extra, undo = APTS_D, dict(foc=True), (lambda: None)
+        else:
+            Xr, Yr = X.to(dev), Y.to(dev)
+            c = _cfg(min_delta=0.01, max_delta=0.5, norm_type=math.inf)
+            cls, extra, undo = APTS_P, {}, _patch_ownership(g, rank)
+        c.glob_opt, c.loc_opt = str(g["glob"]), str(g["loc"])
+        c = cls.setup_APTS_hparams(c)
+        opt = cls(model.parameters(), model=model, criterion=nn.CrossEntropyLoss(), device=dev, nr_models=ws,
+                  glob_opt=c.glob_opt, glob_opt_hparams=c.glob_opt_hparams, loc_opt=c.loc_opt,
+                  loc_opt_hparams=c.loc_opt_hparams, glob_pass=True, norm_type=c.norm_type, max_loc_iters=3,
+                  max_glob_iters=1, tol=1e-6, **extra, **c.apts_params)
+        undo()
+        step = lambda: opt.step(Xr, Yr)  # noqa: E731
+    losses, deltas, gev = [], [], []
+    for _ in range(int(g["steps"])):
+        losses.append(float(step()))
+        deltas.append(float(opt.delta))
+        gev.append(float(opt.grad_evals))
+    w = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).double()
+    wmax, wmin = w.clone(), w.clone()
+    dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(wmin, op=dist.ReduceOp.MIN)
+    gl, gd, ge = np.asarray(g["loss"]), np.asarray(g["delta"]), np.asarray(g["grad_evals"])
+    wf = torch.from_numpy(g["w_final"]).double().to(dev)
+    return dict(case=name, steps=int(g["steps"]),
+                max_rel_loss_err=float(np.max(np.abs(np.asarray(losses) - gl) / np.abs(gl))),
+                deltas_identical=bool(np.allclose(deltas, gd, rtol=1e-9, atol=0)),
+                grad_evals_identical=bool(np.allclose(gev, ge, rtol=0, atol=1e-9)),
+                ranks_identical=bool(torch.equal(wmax, wmin)),
+                rel_w_final_err=float((w - wf).norm() / wf.norm()))
+
+
+def run(rank, ws, dev):
+    """Returns (summary dict, ok).  Every rank must call it (collectives inside)."""
+    cases = CASES.get(ws)
+    if not cases:
+        return {"skipped": f"no committed {ws}-rank golden"}, True
+    out, ok = [], True
+    for name, kind, tol in cases:
+        r = _run_case(name, kind, rank, ws, dev)
+        r["loss_tol"] = tol
+        r["ok"] = bool(r["max_rel_loss_err"] <= tol and r["deltas_identical"] and r["grad_evals_identical"]
+                       and r["ranks_identical"])
+        ok = ok and r["ok"]
+        out.append(r)
+    worst = max(out, key=lambda r: r["max_rel_loss_err"])
+    return {"case": worst["case"], "max_rel_loss_err": worst["max_rel_loss_err"],
+            "deltas_identical": all(r["deltas_identical"] for r in out),
+            "grad_evals_identical": all(r["grad_evals_identical"] for r in out),
+            "ranks_identical": all(r["ranks_identical"] for r in out), "ok": ok, "cases": out,
+            "golden_source": "unmodified reference on gloo ranks (tests/golden/gen_golden.py)"}, ok
