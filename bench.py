@@ -175,7 +175,10 @@ def build_job(name, device, world, rank, labels="random", batch=None):
             xd = b[0].to(device, non_blocking=True).double().requires_grad_(True)   # trainer.py:987-989
             crit.current_x = xd
             return xd, b[1].to(device, non_blocking=True).double()
-        job = Job(name, model, opt, pin(x, flag), lambda b: opt.step(inputs=b[0], labels=b[1]), upload)
+        def pinn_step(b):
+            crit.current_x = b[0]                            # trainer.py:997-998: set for every batch
+            return opt.step(inputs=b[0], labels=b[1])
+        job = Job(name, model, opt, pin(x, flag), pinn_step, upload)
     elif name == "deeponet_tr":
         from dd4ml_b200 import TR
         from dd4ml_b200.utility.optimizer_utils import get_tr_hparams

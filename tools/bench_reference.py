@@ -125,6 +125,7 @@ def build(config: str, rank: int, ws: int, per_rank_batch: int, overrides: dict)
 
 
 def _worker(rank, ws, port, config, per_rank_batch, overrides, steps, warmup, threads, q):
+    os.dup2(2, 1)                       # the reference prints banners (dprint); bench.py's stdout is one JSON line
     import torch
     import torch.distributed as dist
     torch.set_num_threads(max(1, threads))
