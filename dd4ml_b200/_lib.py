@@ -137,7 +137,9 @@ class Lib:
 
 
 # kernels launched per entry point
-_LAUNCHES = {"state_init": 2, "lsr1_B": 2, "version": 0, "error_string": 0}
+# (the reduction kernel + the one-warp k-space kernel for the entry points that solve in k-space)
+_LAUNCHES = {"state_init": 2, "lsr1_B": 3, "tr_propose": 2, "lssr1_begin": 2, "tr_decide": 2, "lsr1_update": 2,
+             "version": 0, "error_string": 0}
 
 _LIB: Lib | None = None
 

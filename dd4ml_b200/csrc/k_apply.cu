@@ -6,7 +6,6 @@ namespace {
 template <class HT, class VT, class WT, int KMAX>
 struct ApplyOp {
     static constexpr int NRED = 1;
-    static constexpr bool SMEM_STATE = false;
     static constexpr int F = 2, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4;
     __host__ __device__ static constexpr bool is_max(int) { return true; }
     dd4ml_state* st;
@@ -78,7 +77,7 @@ struct ApplyOp {
             st_v<V, WT>(w, i, wv);
         }
     }
-    __device__ void finalize(const double* s, ks::Scratch*, dd4ml_state* t) { t->pmax[0] = s[0]; }
+    __device__ void finalize(const double* s, dd4ml_state* t) { t->pmax[0] = s[0]; }
 };
 
 }  // namespace

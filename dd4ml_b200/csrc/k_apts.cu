@@ -6,7 +6,6 @@ namespace {
 template <class VT>
 struct ResidualOp {
     static constexpr int NRED = 0;
-    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     const VT* Gg;
     const VT* Gl;
@@ -27,13 +26,12 @@ struct ResidualOp {
         st_v<V, VT>(gl0, i, b);
         if (resid != nullptr) st_v<V, VT>(resid, i, r);
     }
-    __device__ void finalize(const double*, ks::Scratch*, dd4ml_state*) {}
+    __device__ void finalize(const double*, dd4ml_state*) {}
 };
 
 template <class VT, class WT>
 struct FocOp {
     static constexpr int NRED = 2;
-    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     dd4ml_state* st;
     const WT* wl;
@@ -59,7 +57,7 @@ struct FocOp {
             acc[1] += r[e] * d;
         }
     }
-    __device__ void finalize(const double* s, ks::Scratch*, dd4ml_state*) {
+    __device__ void finalize(const double* s, dd4ml_state*) {
         st->foc_dd[0] = s[0];
         st->foc_rd[0] = s[1];
         const double l = ld_scalar(loss_in, lt);
@@ -74,7 +72,6 @@ struct FocOp {
 template <class WT, class BT>
 struct PackOp {
     static constexpr int NRED = 0;
-    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     BT* buf;
     const WT* wl;
@@ -102,13 +99,12 @@ struct PackOp {
         for (int e = 0; e < V; ++e) a[e] = rnd<WT>(a[e] - b[e]);
         st_v<V, BT>(buf, i, a);
     }
-    __device__ void finalize(const double*, ks::Scratch*, dd4ml_state*) {}
+    __device__ void finalize(const double*, dd4ml_state*) {}
 };
 
 template <class WT, class BT>
 struct AptsTrialOp {
     static constexpr int NRED = 0;
-    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     WT* w;
     const WT* w0;
@@ -134,13 +130,12 @@ struct AptsTrialOp {
         }
         st_v<V, WT>(w, i, a);
     }
-    __device__ void finalize(const double*, ks::Scratch*, dd4ml_state*) {}
+    __device__ void finalize(const double*, dd4ml_state*) {}
 };
 
 template <class VT, class WT>
 struct ControlOp {
     static constexpr int NRED = 2;
-    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
     const void* f0p;
@@ -179,7 +174,7 @@ struct ControlOp {
             st_v<V, WT>(w, i, a);
         }
     }
-    __device__ void finalize(const double* s, ks::Scratch*, dd4ml_state*) {
+    __device__ void finalize(const double* s, dd4ml_state*) {
         const bool acc = (lt == 0) ? ks::apts_control<float>(st, f0, f1, pred) : ks::apts_control<double>(st, f0, f1, pred);
         if (acc) { st->out_gg[0] = s[0]; st->out_ginf[0] = s[1]; }
         st->aux[0] = auxp ? ld_scalar(auxp, pt) : 0.0;

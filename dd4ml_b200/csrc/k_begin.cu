@@ -6,7 +6,6 @@ namespace {
 template <class HT, class VT, class WT, int KMAX>
 struct LssrBeginOp {
     static constexpr int NRED = 7 + 6 * KMAX;
-    static constexpr bool SMEM_STATE = true;
     // KMAX = 10: 24 streams x 4 KB leave two stages in the ring; half tiles (4 stages) measured 0.50 -> 0.59
     // of peak here, but lose on the ops with fewer streams (twice the loop overhead per element)
     static constexpr int F = 4, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = KMAX > 6 ? 2 : 4;
@@ -100,7 +99,7 @@ struct LssrBeginOp {
         st_v<V, WT>(old_w, i, wv);
         st_v<V, VT>(prev_g, i, gv);
     }
-    __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
+    __device__ void finalize(const double* s, dd4ml_state* t) {   // chain + solve: k-space kernel (KT_BEGIN)
         if (rad[0] >= 0.0) { t->delta[0] = rad[0]; t->min_delta[0] = rad[1]; t->max_delta[0] = rad[2]; }
         t->gg[0] = s[0];
         t->ginf[0] = s[1];
@@ -109,9 +108,7 @@ struct LssrBeginOp {
         t->pair_tried[0] = 0.0;
         t->pair_ok[0] = 0.0;
         t->err[0] = 0.0;
-        // lssr1_tr.py:509: the convergence test precedes the memory update
-        const double gn = (double)(VT)sqrt(s[0]);
-        if (pair && gn > t->tol[0]) {
+        if (pair) {
             t->c_ss[0] = s[2]; t->c_sy[0] = s[3]; t->c_yy[0] = s[4];
             t->c_sg[0] = s[5]; t->c_yg[0] = s[6];
             for (int j = 0; j < sl.k; ++j) {
@@ -120,17 +117,7 @@ struct LssrBeginOp {
                 t->c_Sy[sl.at(j)] = s[7 + 4 * KMAX + j];
                 t->c_Yy[sl.at(j)] = s[7 + 5 * KMAX + j];
             }
-            const double tol = t->tol[0];
-            if (sqrt(s[2]) > tol && sqrt(s[4]) > tol) {  // lssr1_tr.py:521
-                t->pair_tried[0] = 1.0;
-                if (ks::lsr1_try_update(t, scr)) { t->Sg[spare] = s[5]; t->Yg[spare] = s[6]; }
-            }
         }
-        const double ninf = t->norm_inf[0];
-        t->norm_inf[0] = 0.0;  // LSSR1_TR forces the 2-norm (lssr1_tr.py:94)
-        if (t->second_order[0] != 0.0 && t->k[0] > 0.0) ks::tr_solve<HT>(t, 1, scr);
-        else ks::tr_solve<VT>(t, 1, scr);
-        t->norm_inf[0] = ninf;
     }
 };
 
@@ -163,9 +150,16 @@ extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void*
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = aligned16(w) && aligned16(old_w) && aligned16(g) && aligned16(prev_g) && aligned16(S) &&
                      aligned16(Y) && ld % 4 == 0;
+    int rc = DD4ML_E_DTYPE;
 #define CALL(HT, VT, WT) \
-    return begin_t<HT, VT, WT>(state, ws, w, old_w, g, prev_g, has_prev, S, Y, loss, lt, n, ld, kcap, vec, delta, \
-                               min_delta, max_delta, s);
-    DT_SWITCH3(ht, vt, wt, CALL)
+    rc = begin_t<HT, VT, WT>(state, ws, w, old_w, g, prev_g, has_prev, S, Y, loss, lt, n, ld, kcap, vec, delta, \
+                             min_delta, max_delta, s);
+    DT_SWITCH3_RC(ht, vt, wt, CALL)
 #undef CALL
+    if (rc) return rc;
+    KTask t{};
+    t.kind = KT_BEGIN;
+    t.ht = ht; t.vt = vt; t.lt = lt;
+    t.has_prev = has_prev;
+    return dd4ml_ks_launch(state, t, s);
 }

@@ -6,7 +6,6 @@ namespace {
 template <class HT, class VT, class WT, int KMAX, bool MEM>
 struct DecideOp {
     static constexpr int NRED = 5 + 4 * KMAX;
-    static constexpr bool SMEM_STATE = true;
     static constexpr int F = 3, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 4; }
     dd4ml_state* st;
@@ -112,7 +111,7 @@ struct DecideOp {
         }
         st_v<V, VT>(gout, i, tv);
     }
-    __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
+    __device__ void finalize(const double* s, dd4ml_state* t) {   // radius / L-SR1 update: k-space kernel (KT_DECIDE)
         t->loss[0] = f0;
         t->trial_loss[0] = f1;
         if (loss_out != nullptr) st_scalar(loss_out, lt, accept ? f1 : f0);
@@ -131,11 +130,6 @@ struct DecideOp {
                 t->c_Yy[sl.at(j)] = s[5 + 3 * KMAX + j];
             }
         }
-        const double so = t->second_order[0];
-        if (!MEM) t->second_order[0] = 0.0;
-        if (lt == 0) ks::tr_finish<float>(t, accept, rho, scr); else ks::tr_finish<double>(t, accept, rho, scr);
-        t->second_order[0] = so;
-        t->solve_valid[0] = 0.0;
     }
 };
 
@@ -143,7 +137,6 @@ struct DecideOp {
 template <class HT, class VT, int KMAX>
 struct UpdateOp {
     static constexpr int NRED = 3 + 4 * KMAX;
-    static constexpr bool SMEM_STATE = true;
     static constexpr int F = 2, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     dd4ml_state* st;
@@ -197,7 +190,7 @@ struct UpdateOp {
         st_v<V, HT>(S + (int64_t)spare * ld, i, sv);
         st_v<V, HT>(Y + (int64_t)spare * ld, i, yv);
     }
-    __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
+    __device__ void finalize(const double* s, dd4ml_state* t) {   // acceptance chain: k-space kernel (KT_UPDATE)
         t->c_ss[0] = s[0]; t->c_sy[0] = s[1]; t->c_yy[0] = s[2];
         for (int j = 0; j < sl.k; ++j) {
             t->c_Ss[sl.at(j)] = s[3 + j];
@@ -205,10 +198,6 @@ struct UpdateOp {
             t->c_Sy[sl.at(j)] = s[3 + 2 * KMAX + j];
             t->c_Yy[sl.at(j)] = s[3 + 3 * KMAX + j];
         }
-        t->err[0] = 0.0;
-        t->pair_tried[0] = 1.0;
-        ks::lsr1_try_update(t, scr);
-        t->solve_valid[0] = 0.0;
     }
 };
 
@@ -260,11 +249,18 @@ int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* tri
     const int copy_old = (loss_out != nullptr && g_old != g_out) ? 1 : 0;   // device-side select mode only
     const bool vec = aligned16(g_trial) && aligned16(g_old) && aligned16(g_out) && aligned16(p) && aligned16(w) &&
                      (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
+    int rc = DD4ML_E_DTYPE;
 #define CALL(HT, VT, WT)                                                                                         \
-    return decide_t<HT, VT, WT>(state, ws, loss, trial_loss, lt, g_trial, g_old, g_out, p, w, S, Y, loss_out, copy_old, \
-                                n, ld, kcap, vec, s);
-    DT_SWITCH3(ht, vt, wt, CALL)
+    rc = decide_t<HT, VT, WT>(state, ws, loss, trial_loss, lt, g_trial, g_old, g_out, p, w, S, Y, loss_out, copy_old, \
+                              n, ld, kcap, vec, s);
+    DT_SWITCH3_RC(ht, vt, wt, CALL)
 #undef CALL
+    if (rc) return rc;
+    KTask t{};
+    t.kind = KT_DECIDE;
+    t.ht = ht; t.vt = vt; t.lt = lt;
+    t.mem = S ? 1 : 0;
+    return dd4ml_ks_launch(state, t, s);
 }
 
 int dd4ml_lsr1_update(double* state, double* ws, const void* s_in, const void* y_in, void* S, void* Y,
@@ -272,9 +268,15 @@ int dd4ml_lsr1_update(double* state, double* ws, const void* s_in, const void* y
     if (!state || !ws || !s_in || !y_in || !S || !Y || n < 0 || kcap > DD4ML_MAXM) return DD4ML_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = aligned16(s_in) && aligned16(y_in) && aligned16(S) && aligned16(Y) && ld % 4 == 0;
-#define CALL(HT, VT) return update_t<HT, VT>(state, ws, s_in, y_in, S, Y, n, ld, kcap, vec, s);
-    DT_SWITCH2(ht, vt, CALL)
+    int rc = DD4ML_E_DTYPE;
+#define CALL(HT, VT) rc = update_t<HT, VT>(state, ws, s_in, y_in, S, Y, n, ld, kcap, vec, s);
+    DT_SWITCH2_RC(ht, vt, CALL)
 #undef CALL
+    if (rc) return rc;
+    KTask t{};
+    t.kind = KT_UPDATE;
+    t.ht = ht; t.vt = vt;
+    return dd4ml_ks_launch(state, t, s);
 }
 
 }  // extern "C"

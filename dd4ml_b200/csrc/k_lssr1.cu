@@ -7,7 +7,6 @@ namespace {
 template <class VT, class WT>
 struct TrialOp {
     static constexpr int NRED = 0;
-    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     WT* w;
     const WT* base;
@@ -25,13 +24,12 @@ struct TrialOp {
         for (int e = 0; e < V; ++e) b[e] += rnd<VT>(alpha * pv[e]);
         st_v<V, WT>(w, i, b);
     }
-    __device__ void finalize(const double*, ks::Scratch*, dd4ml_state*) {}
+    __device__ void finalize(const double*, dd4ml_state*) {}
 };
 
 template <class VT>
 struct EvalOp {
     static constexpr int NRED = 3;
-    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 2; }
     dd4ml_state* st;
     const VT* g;
@@ -55,7 +53,7 @@ struct EvalOp {
         }
         if (gs != nullptr) st_v<V, VT>(gs, i, gv);
     }
-    __device__ void finalize(const double* s, ks::Scratch*, dd4ml_state* t) {
+    __device__ void finalize(const double* s, dd4ml_state* t) {
         t->deriv[0] = s[0];
         t->out_gg[0] = s[1];
         t->out_ginf[0] = s[2];

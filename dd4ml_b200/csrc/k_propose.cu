@@ -6,7 +6,6 @@ namespace {
 template <class HT, class VT, int KMAX>
 struct ProposeOp {
     static constexpr int NRED = 2 + 2 * KMAX;
-    static constexpr bool SMEM_STATE = true;
     static constexpr int F = 1, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
@@ -49,14 +48,10 @@ struct ProposeOp {
                 }
             }
     }
-    __device__ void finalize(const double* s, ks::Scratch* scr, dd4ml_state* t) {
+    __device__ void finalize(const double* s, dd4ml_state* t) {   // the solve itself: k-space kernel (KT_SOLVE / KT_B / KT_SMW)
         t->gg[0] = s[0];
         t->ginf[0] = s[1];
         for (int j = 0; j < sl.k; ++j) { t->Sg[sl.at(j)] = s[2 + j]; t->Yg[sl.at(j)] = s[2 + KMAX + j]; }
-        if (mode == 2) ks::lsr1_B_coefs(t, scr);
-        else if (mode == 3) ks::smw_coefs(t, scr);
-        else if (sl.k > 0) ks::tr_solve<HT>(t, mode, scr);   // OBS works in the dtype of Psi (obs.py:88)
-        else ks::tr_solve<VT>(t, mode, scr);
     }
 };
 
@@ -85,7 +80,14 @@ extern "C" int dd4ml_tr_propose(double* state, double* ws, const void* g, const 
     if (!state || !ws || !g || n < 0 || kcap > DD4ML_MAXM) return DD4ML_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const bool vec = aligned16(g) && (!S || (aligned16(S) && aligned16(Y) && ld % 4 == 0));
-#define CALL(HT, VT) return propose_t<HT, VT>(state, ws, g, S, Y, n, ld, mode, kcap, vec, s);
-    DT_SWITCH2(ht, vt, CALL)
+    int rc = DD4ML_E_DTYPE;
+#define CALL(HT, VT) rc = propose_t<HT, VT>(state, ws, g, S, Y, n, ld, mode, kcap, vec, s);
+    DT_SWITCH2_RC(ht, vt, CALL)
 #undef CALL
+    if (rc) return rc;
+    KTask t{};
+    t.kind = mode == 2 ? KT_B : (mode == 3 ? KT_SMW : KT_SOLVE);
+    t.mode = mode;
+    t.ht = ht; t.vt = vt;
+    return dd4ml_ks_launch(state, t, s);
 }

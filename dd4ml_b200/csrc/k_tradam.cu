@@ -32,7 +32,6 @@ __device__ __forceinline__ T adam_dir(T m, T v, T bc1, T bc2, T eps) {
 template <class VT>
 struct AdamMomentsOp {
     static constexpr int NRED = 2;
-    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
     const VT* g;
@@ -65,7 +64,7 @@ struct AdamMomentsOp {
         st_v<V, VT>(m, i, mo);
         st_v<V, VT>(v, i, vo);
     }
-    __device__ void finalize(const double* s, ks::Scratch*, dd4ml_state* t) {
+    __device__ void finalize(const double* s, dd4ml_state* t) {
         const double len = (double)(VT)(norm_inf ? s[1] : s[0]);   // .item() of a VT tensor
         t->pnorm[0] = len;
         t->aux[0] = (len > lr) ? lr / len : lr;                     // tradam.py:104-107
@@ -75,7 +74,6 @@ struct AdamMomentsOp {
 template <class VT, class WT>
 struct AdamApplyOp {
     static constexpr int NRED = 0;
-    static constexpr bool SMEM_STATE = false;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     dd4ml_state* st;
     const VT* m;
@@ -104,7 +102,7 @@ struct AdamApplyOp {
         if (step != nullptr) st_v<V, VT>(step, i, so);
         st_v<V, WT>(w, i, wo);
     }
-    __device__ void finalize(const double*, ks::Scratch*, dd4ml_state*) {}
+    __device__ void finalize(const double*, dd4ml_state*) {}
 };
 
 }  // namespace

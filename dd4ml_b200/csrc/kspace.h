@@ -1,11 +1,23 @@
-// k-space routines of the trust-region step: everything that happens between the
-// streaming reductions over the n-vectors and the streaming output pass.
+// k-space routines of the trust-region step: everything that happens between the streaming
+// reductions over the n-vectors and the streaming output pass.
 //
-// All inputs are O(k^2) numbers (Gram blocks of the L-SR1 pairs, Psi^T g, g^T g)
-// held in the device state block; the routines run in ONE thread of the last CTA of
-// the reduction kernel ("small m x m inner solve kept in one CTA").  The file is
-// plain C++ guarded for host compilation as well, so tests/hostshim can run the
-// same source on the CPU against the oracle.
+// All inputs are O(k^2) numbers (Gram blocks of the L-SR1 pairs, Psi^T g, g^T g) held in the device
+// state block.  The routines run in the ONE-WARP k-space kernel (k_kspace.cu) that follows every
+// reduction kernel ("small m x m inner solve kept in one CTA"): the k x k matrices live in shared
+// memory and every O(k^2)/O(k^3) step is a *parallel region* over matrix elements / rows / columns /
+// Jacobi rotation pairs, so the dependent chain is O(k) steps per factorisation instead of O(k^3)
+// scalar operations in one thread.  The code is loop based and compact on purpose: it is executed
+// once per launch right after the closure's kernels have evicted the instruction cache, so its
+// footprint, not its flop count, sets its latency.
+//
+// Execution model (also what lets tests/hostshim compile this file for the CPU):
+//   KS_PAR(i, n) { body }  KS_SYNC();      a parallel region: iterations are independent -- an iteration
+//                                          never reads what another iteration of the same region writes
+//   everything else                        uniform code, executed redundantly by all lanes; shared state is
+//                                          written by the master lane only (KS_MASTER) and never read back
+//                                          before the next KS_SYNC()
+// On the device KS_PAR strides the lanes of the warp and KS_SYNC is __syncwarp(); on the host KS_PAR is a
+// plain loop and KS_SYNC a no-op, which is the same program by the independence rule.
 //
 // Reference behaviour restated here (cruzas/DD4ML):
 //   LSR1.precompute / B / update_memory      optimizers/lsr1.py:53-198
@@ -13,9 +25,9 @@
 //   solve_tr_first_order / second_order      utility/optimizer_utils.py:197-307
 //   TR.step ratio test and radius update     optimizers/tr.py:186-221
 //   LSSR1_TR clip-to-radius / descent flip   optimizers/lssr1_tr.py:563-587
-// Linear algebra (Cholesky, LU, symmetric eigen-decomposition) runs in double;
-// the quantities the reference thresholds or iterates on in its working dtype
-// (Lambda, a_j, the Newton iteration, rho) are rounded to that dtype T first.
+// Linear algebra (Cholesky, LU, symmetric eigen-decomposition) runs in double; the quantities the
+// reference thresholds or iterates on in its working dtype (Lambda, a_j, the Newton iteration, rho) are
+// rounded to that dtype T first.
 #pragma once
 #include <math.h>
 
@@ -23,15 +35,36 @@
 
 #ifdef __CUDACC__
 #define KS_FN __host__ __device__
+#define KS_BIG __host__ __device__ __noinline__    // one copy of every large routine: code size is latency here
+#define KS_LOOP _Pragma("unroll 1")
 #else
 #define KS_FN
+#define KS_BIG
+#define KS_LOOP
 #endif
 #if defined(__CUDA_ARCH__)
 #define KS_CLOCK() ((double)clock64())
 #define KS_RSQRT(x) rsqrt(x)
+#define KS_TID ((int)threadIdx.x)
+#define KS_NT ((int)blockDim.x)
+#define KS_SYNC() __syncwarp()
 #else
 #define KS_CLOCK() 0.0
 #define KS_RSQRT(x) (1.0 / sqrt(x))
+#define KS_TID 0
+#define KS_NT 1
+#define KS_SYNC() ((void)0)
+#endif
+#define KS_PAR(i, n) KS_LOOP for (int i = KS_TID; i < (n); i += KS_NT)
+#define KS_MASTER if (KS_TID == 0)
+// 2-D region over a k x k block: slots e = i*M + j with the constant leading dimension M (division by a
+// constant, no runtime integer division), entries j >= k idle.  Usage: KS_PAR2(i, j, k) { ... } KS_END2
+#define KS_PAR2(i, j, k) KS_LOOP for (int e_ = KS_TID; e_ < (k) * M; e_ += KS_NT) { const int i = e_ / M, j = e_ - i * M; if (j < (k))
+#define KS_END2 }
+#ifdef __CUDACC__
+#define KS_UNROLL _Pragma("unroll")
+#else
+#define KS_UNROLL
 #endif
 
 namespace ks {
@@ -41,186 +74,315 @@ constexpr int MS = DD4ML_MAXS;
 constexpr double OBS_TOL = 1e-6;  // obs.py:29
 
 KS_FN inline bool finite(double x) { return x == x && fabs(x) <= 1.79769313486231570e308; }
+// IEEE double division / square root expand to ~30 instructions each: one out-of-line copy
+KS_BIG inline double ddiv(double a, double b) { return a / b; }
+KS_BIG inline double dsqrt(double x) { return sqrt(x); }
+// Round to the reference's working dtype (float32 or float64).  A float32 operation on float32
+// operands equals the float64 operation rounded to float32 (53 >= 2*24 + 2 bits: no double-rounding
+// error for + - * / sqrt), so `rT(a op b, f32)` IS the reference's float32 arithmetic.
+KS_FN inline double rT(double x, bool f32) { return f32 ? (double)(float)x : x; }
 KS_FN inline float ks_sqrt(float x) { return sqrtf(x); }
 KS_FN inline double ks_sqrt(double x) { return sqrt(x); }
 
-// ---- dense helpers on row-major k x k blocks with leading dimension M ----------
-// R upper triangular with R^T R = G (torch.linalg.cholesky(upper=True)).
-KS_FN inline bool chol_upper(const double* G, int k, double* R) {
-    for (int i = 0; i < k * M; ++i) R[i] = 0.0;
+// Work arrays of the k-space routines: shared memory of the k-space kernel (row-major, leading
+// dimension M).
+struct Scratch {
+    double Minv[M * M];  // diag(S^T Y) + L + L^T - gamma S^T S + tol*||.||_F I   (lsr1.py:168-179)
+    double G[M * M];     // Psi^T Psi
+    double R[M * M], LU[M * M], MR[M * M], RMR[M * M], U[M * M], V[M * M], RinvU[M * M], W[M * M];
+    double D[M], Dw[M], b[M], x[M], z[M], wv[M], Gw[M], bs[M], by[M], ad[M + 1];
+    double Ld[M + 1], Ad[M + 1];   // Lambda, a in the working dtype (T = double)
+    float Lf[M + 1], Af[M + 1];    //                                 (T = float)
+    double rc[M], rs[M];           // Jacobi rotations of one round
+    int rp[M], rq[M], rank[M];
+    int piv[M], pw[M];
+};
+template <class T> struct LamA;
+template <> struct LamA<float> {
+    KS_FN static float* lam(Scratch* ws) { return ws->Lf; }
+    KS_FN static float* a(Scratch* ws) { return ws->Af; }
+};
+template <> struct LamA<double> {
+    KS_FN static double* lam(Scratch* ws) { return ws->Ld; }
+    KS_FN static double* a(Scratch* ws) { return ws->Ad; }
+};
+
+// sum_{i<k} a[i*sa] * b[i*sb].  ONE out-of-line copy with a runtime loop: the k-space kernel is bound by
+// instruction issue / fetch of a single warp (ncu: ~5 cycles per instruction, half of the stall samples
+// `no_instruction`), so the dynamic instruction count and the code footprint are what matter -- a
+// predicated unroll to M terms executes M/k times the instructions and was measured slower.
+KS_BIG inline double dots(const double* a, int sa, const double* b, int sb, int k) {
+    double s = 0.0;
+    KS_LOOP
+    for (int i = 0; i < k; ++i) s += a[i * sa] * b[i * sb];
+    return s;
+}
+KS_FN inline double dotk(const double* a, const double* b, int k) { return dots(a, 1, b, 1, k); }
+
+// ---- dense helpers on row-major k x k blocks with leading dimension M (collective) -----------
+// R upper triangular with R^T R = G (torch.linalg.cholesky(upper=True)).  One column per step:
+// the pivot is uniform scalar work, the row to its right a parallel region.
+KS_BIG inline bool chol_upper(const double* G, int k, double* R) {
+    KS_PAR(e, k * M) R[e] = 0.0;
+    KS_SYNC();
+    KS_LOOP
     for (int j = 0; j < k; ++j) {
-        double s = G[j * M + j];
-        for (int i = 0; i < j; ++i) s -= R[i * M + j] * R[i * M + j];
+        const double s = G[j * M + j] - dots(R + j, M, R + j, M, j);
         if (!(s > 0.0) || !finite(s)) return false;
-        double d = sqrt(s);
-        R[j * M + j] = d;
-        for (int c = j + 1; c < k; ++c) {
-            double t = G[j * M + c];
-            for (int i = 0; i < j; ++i) t -= R[i * M + j] * R[i * M + c];
-            R[j * M + c] = t / d;
+        const double d = dsqrt(s);
+        KS_PAR(c, k) {
+            if (c == j) R[j * M + j] = d;
+            else if (c > j) R[j * M + c] = ddiv(G[j * M + c] - dots(R + j, M, R + c, M, j), d);
         }
+        KS_SYNC();
     }
     return true;
 }
 
-// In-place LU with partial pivoting (torch.linalg.solve = getrf/getrs).
-KS_FN inline bool lu_factor(double* A, int k, int* piv) {
+// In-place LU with partial pivoting (torch.linalg.solve = getrf/getrs): pivot search uniform; row
+// swap, multipliers and the rank-1 update of the trailing block are parallel regions.
+KS_BIG inline bool lu_factor(double* A, int k, int* piv) {
+    KS_LOOP
     for (int c = 0; c < k; ++c) {
         int p = c;
         double best = fabs(A[c * M + c]);
+        KS_LOOP
         for (int r = c + 1; r < k; ++r) {
-            double v = fabs(A[r * M + c]);
+            const double v = fabs(A[r * M + c]);
             if (v > best) { best = v; p = r; }
         }
-        piv[c] = p;
         if (best == 0.0 || !finite(best)) return false;
-        if (p != c)
-            for (int j = 0; j < k; ++j) { double t = A[c * M + j]; A[c * M + j] = A[p * M + j]; A[p * M + j] = t; }
-        double inv = 1.0 / A[c * M + c];
-        for (int r = c + 1; r < k; ++r) {
-            double f = A[r * M + c] * inv;
-            A[r * M + c] = f;
-            for (int j = c + 1; j < k; ++j) A[r * M + j] -= f * A[c * M + j];
+        KS_SYNC();                      // every lane has read column c before rows move
+        KS_PAR(j, k) {
+            if (j == 0) piv[c] = p;
+            if (p != c) { const double t = A[c * M + j]; A[c * M + j] = A[p * M + j]; A[p * M + j] = t; }
         }
+        KS_SYNC();
+        const double inv = ddiv(1.0, A[c * M + c]);
+        KS_PAR(r, k) { if (r > c) A[r * M + c] *= inv; }          // multipliers
+        KS_SYNC();
+        KS_PAR2(r, j, k) {              // trailing block
+            if (r > c && j > c) A[r * M + j] -= A[r * M + c] * A[c * M + j];
+        } KS_END2
+        KS_SYNC();
     }
     return true;
 }
 
-KS_FN inline void lu_solve(const double* LU, const int* piv, int k, double* b) {
-    for (int c = 0; c < k; ++c) {
-        int p = piv[c];
-        if (p != c) { double t = b[c]; b[c] = b[p]; b[p] = t; }
+// v <- A^{-1} v from the factorisation (per lane, not collective); v has stride ldv
+KS_BIG inline void lu_solve_vec(const double* LU, const int* piv, int k, double* v, int ldv) {
+    KS_LOOP
+    for (int i = 0; i < k; ++i) {
+        const int p = piv[i];
+        if (p != i) { const double t = v[i * ldv]; v[i * ldv] = v[p * ldv]; v[p * ldv] = t; }
     }
-    for (int r = 1; r < k; ++r) {
-        double s = b[r];
-        for (int j = 0; j < r; ++j) s -= LU[r * M + j] * b[j];
-        b[r] = s;
-    }
+    KS_LOOP
+    for (int r = 1; r < k; ++r) v[r * ldv] -= dots(LU + r * M, 1, v, ldv, r);
+    KS_LOOP
     for (int r = k - 1; r >= 0; --r) {
-        double s = b[r];
-        for (int j = r + 1; j < k; ++j) s -= LU[r * M + j] * b[j];
-        b[r] = s / LU[r * M + r];
+        const double s = v[r * ldv] - dots(LU + r * M + r + 1, 1, v + (r + 1) * ldv, ldv, k - r - 1);
+        v[r * ldv] = ddiv(s, LU[r * M + r]);
     }
 }
 
-// Cyclic Jacobi for a symmetric k x k matrix.  On exit w ascending, V[:, j] the
-// eigenvector of w[j], each with its largest-|.| component positive (lowest index
-// on ties): the documented sign convention of this implementation.
-KS_FN inline int jacobi_eigh(double* A, int k, double* w, double* V) {
-    for (int i = 0; i < k; ++i)
-        for (int j = 0; j < k; ++j) V[i * M + j] = (i == j) ? 1.0 : 0.0;
+// X[:, c] <- A^{-1} X[:, c] for c < ncols (one right-hand side per lane).  Collective.
+KS_FN inline void lu_solve_cols(const double* LU, const int* piv, int k, double* X, int ldx, int ncols) {
+    KS_PAR(c, ncols) lu_solve_vec(LU, piv, k, X + c, ldx);
+    KS_SYNC();
+}
+
+// Jacobi eigen-decomposition of a symmetric k x k matrix with the round-robin (tournament) ordering:
+// the floor(k/2) rotations of a round touch disjoint index pairs and are applied together -- k-1 (k)
+// rounds per sweep instead of k(k-1)/2 dependent rotations.  On exit w ascending, U[:, j] the
+// eigenvector of w[j], each with its largest-|.| component positive (lowest index on ties): the
+// documented sign convention of this implementation.  A is destroyed.
+// The rotation angle is computed in float32 on exponent-normalised inputs (any angle keeps the
+// transformation orthogonal as long as c = 1/sqrt(1 + t^2) and s = t c are formed in double; a 1e-7
+// relative error of t only leaves 1e-7 of the pivot behind for the next sweep), which takes the
+// double-precision division and square root off the dependent chain of every round.
+KS_BIG inline int jacobi_eigh(double* A, int k, double* w, double* U, Scratch* ws) {
+    double* V = ws->V;
+    KS_PAR2(i, j, k) { V[i * M + j] = (i == j) ? 1.0 : 0.0; } KS_END2
+    KS_SYNC();
+    const int n = k + (k & 1);          // players of the tournament (one dummy when k is odd)
+    const int half = n >> 1;
     int sweeps = 0;
-    for (int sweep = 0; sweep < 64; ++sweep) {
+    KS_LOOP
+    for (int sweep = 0; sweep < 64 && k > 1; ++sweep) {
+        KS_PAR(i, k) {                  // off-diagonal / diagonal mass, one row per lane
+            double o = 0.0;         // (summed directly: total - diagonal would cancel at the 1e-26 threshold)
+            KS_LOOP
+            for (int j = 0; j < k; ++j)
+                if (j != i) o += A[i * M + j] * A[i * M + j];
+            ws->rc[i] = o;
+            ws->rs[i] = A[i * M + i] * A[i * M + i];
+        }
+        KS_SYNC();
         double off = 0.0, diag = 0.0;
-        for (int i = 0; i < k; ++i) {
-            diag += A[i * M + i] * A[i * M + i];
-            for (int j = i + 1; j < k; ++j) off += A[i * M + j] * A[i * M + j];
-        }
-        // off-diagonal mass below 1e-26 of the diagonal mass: eigenvalues converged to ~1e-26
-        // relative (Jacobi converges quadratically), eigenvectors to ~1e-13
-        if (off <= 1e-26 * diag || off == 0.0) break;
+        KS_LOOP
+        for (int i = 0; i < k; ++i) { off += ws->rc[i]; diag += ws->rs[i]; }
+        KS_SYNC();                      // rc / rs are reused for the rotations
+        // off-diagonal mass (each entry counted twice) below 1e-26 of the diagonal mass: eigenvalues
+        // converged to ~1e-26 relative (Jacobi converges quadratically), eigenvectors to ~1e-13
+        if (0.5 * off <= 1e-26 * diag || off == 0.0) break;
         ++sweeps;
-        for (int p = 0; p < k - 1; ++p)
-            for (int q = p + 1; q < k; ++q) {
-                double apq = A[p * M + q];
-                if (apq == 0.0) continue;
-                // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq),
-                // written with one division and one square root
-                const double d = A[q * M + q] - A[p * M + p];
-                const double a2 = 2.0 * apq;
-                const double sg = ((d >= 0.0) == (a2 >= 0.0)) ? 1.0 : -1.0;
-                const double t = sg * fabs(a2) / (fabs(d) + sqrt(d * d + a2 * a2));
-                const double c = KS_RSQRT(t * t + 1.0), s = t * c;
-                // Each update loads its two vectors into registers first (constant trip count M,
-                // predicated on r < k): the loads issue back to back instead of one dependent
-                // shared-memory round trip per element -- the rotation is ~4x faster for k = 10.
-                double u[M], v[M];
-#pragma unroll
-                for (int r = 0; r < M; ++r)   // columns p, q of A
-                    if (r < k) { u[r] = A[r * M + p]; v[r] = A[r * M + q]; }
-#pragma unroll
-                for (int r = 0; r < M; ++r)
-                    if (r < k) { A[r * M + p] = c * u[r] - s * v[r]; A[r * M + q] = s * u[r] + c * v[r]; }
-#pragma unroll
-                for (int r = 0; r < M; ++r)   // rows p, q of A
-                    if (r < k) { u[r] = A[p * M + r]; v[r] = A[q * M + r]; }
-#pragma unroll
-                for (int r = 0; r < M; ++r)
-                    if (r < k) { A[p * M + r] = c * u[r] - s * v[r]; A[q * M + r] = s * u[r] + c * v[r]; }
-#pragma unroll
-                for (int r = 0; r < M; ++r)
-                    if (r < k) { u[r] = V[r * M + p]; v[r] = V[r * M + q]; }
-#pragma unroll
-                for (int r = 0; r < M; ++r)
-                    if (r < k) { V[r * M + p] = c * u[r] - s * v[r]; V[r * M + q] = s * u[r] + c * v[r]; }
+        KS_LOOP
+        for (int round = 0; round < n - 1; ++round) {
+            KS_PAR(t, half) {           // rotation of pair t of this round
+                int p, q;
+                if (t == 0) { p = n - 1; q = round; }
+                else {
+                    p = round + t; if (p >= n - 1) p -= n - 1;
+                    q = round - t; if (q < 0) q += n - 1;
+                }
+                if (p > q) { const int u = p; p = q; q = u; }
+                double c = 1.0, s = 0.0;
+                if (q < k) {
+                    const double apq = A[p * M + q];
+                    if (apq != 0.0) {
+                        // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq)
+                        const double d = A[q * M + q] - A[p * M + p];
+                        const double a2 = 2.0 * apq;
+                        int ex;
+                        (void)frexp(fmax(fabs(d), fabs(a2)), &ex);
+                        const float df = (float)ldexp(d, -ex), af = (float)ldexp(a2, -ex);
+                        const float tf = fabsf(af) / (fabsf(df) + sqrtf(df * df + af * af));
+                        const double tt = ((d >= 0.0) == (a2 >= 0.0)) ? (double)tf : -(double)tf;
+                        c = KS_RSQRT(tt * tt + 1.0);
+                        s = tt * c;
+                    }
+                }
+                ws->rp[t] = p; ws->rq[t] = q; ws->rc[t] = c; ws->rs[t] = s;
             }
-    }
-    for (int i = 0; i < k; ++i) w[i] = A[i * M + i];
-    for (int i = 0; i < k - 1; ++i) {  // selection sort, ascending
-        int m = i;
-        for (int j = i + 1; j < k; ++j)
-            if (w[j] < w[m]) m = j;
-        if (m != i) {
-            double t = w[i]; w[i] = w[m]; w[m] = t;
-            for (int r = 0; r < k; ++r) { double u = V[r * M + i]; V[r * M + i] = V[r * M + m]; V[r * M + m] = u; }
+            KS_SYNC();
+            KS_PAR2(t, r, k) {          // A <- A J, V <- V J: entry pairs (r, p), (r, q) of every row r
+                if (t < half) {
+                    const int p = ws->rp[t], q = ws->rq[t];
+                    if (q < k) {
+                        const double c = ws->rc[t], s = ws->rs[t];
+                        const double arp = A[r * M + p], arq = A[r * M + q];
+                        const double vrp = V[r * M + p], vrq = V[r * M + q];
+                        A[r * M + p] = c * arp - s * arq;
+                        A[r * M + q] = s * arp + c * arq;
+                        V[r * M + p] = c * vrp - s * vrq;
+                        V[r * M + q] = s * vrp + c * vrq;
+                    }
+                }
+            } KS_END2
+            KS_SYNC();
+            KS_PAR2(t, r, k) {          // A <- J^T A: entry pairs (p, r), (q, r) of every column r
+                if (t < half) {
+                    const int p = ws->rp[t], q = ws->rq[t];
+                    if (q < k) {
+                        const double c = ws->rc[t], s = ws->rs[t];
+                        const double apr = A[p * M + r], aqr = A[q * M + r];
+                        A[p * M + r] = c * apr - s * aqr;
+                        A[q * M + r] = s * apr + c * aqr;
+                    }
+                }
+            } KS_END2
+            KS_SYNC();
         }
     }
-    for (int j = 0; j < k; ++j) {
+    // ascending order through ranks (stable on ties), then the sign convention per column
+    KS_PAR(j, k) {
+        const double wj = A[j * M + j];
+        int r = 0;
+        KS_LOOP
+        for (int i = 0; i < k; ++i) {
+            const double wi = A[i * M + i];
+            r += (wi < wj || (wi == wj && i < j)) ? 1 : 0;
+        }
+        ws->rank[j] = r;
+        w[r] = wj;
+    }
+    KS_SYNC();
+    KS_PAR(j, k) {
+        const int r = ws->rank[j];
         int im = 0;
         double best = -1.0;
-        for (int r = 0; r < k; ++r)
-            if (fabs(V[r * M + j]) > best) { best = fabs(V[r * M + j]); im = r; }
-        if (V[im * M + j] < 0.0)
-            for (int r = 0; r < k; ++r) V[r * M + j] = -V[r * M + j];
+        KS_LOOP
+        for (int i = 0; i < k; ++i)
+            if (fabs(V[i * M + j]) > best) { best = fabs(V[i * M + j]); im = i; }
+        const double sg = (V[im * M + j] < 0.0) ? -1.0 : 1.0;
+        KS_LOOP
+        for (int i = 0; i < k; ++i) U[i * M + r] = sg * V[i * M + j];
     }
+    KS_SYNC();
     return sweeps;
 }
 
-// ---- secular equation, in the reference's working dtype T (obs.py:184-254) -----
+// ---- secular equation, in the reference's working dtype T (obs.py:184-254); per-lane, pure ----
 template <class T>
-KS_FN inline void phibar_fg(T sigma, const T* Lam, const T* a, int m, T delta, T tol, T& f, T& g, bool& deg) {
-    deg = false;
-    for (int j = 0; j < m; ++j) {
-        T D = Lam[j] + sigma;
-        if (fabs(a[j]) < tol || fabs(D) < tol) deg = true;
+struct Secular {
+    const T* L;
+    const T* A;
+    int m;
+    T delta, tol;
+    KS_FN void load(const T* Lam, const T* a, int m_, T delta_, T tol_) { L = Lam; A = a; m = m_; delta = delta_; tol = tol_; }
+    KS_FN bool degenerate(T sigma) const {
+        bool deg = false;
+        KS_LOOP
+        for (int j = 0; j < m; ++j) {
+            const T D = L[j] + sigma;
+            if (fabs(A[j]) < tol || fabs(D) < tol) deg = true;
+        }
+        return deg;
     }
-    if (deg) {  // obs.py:242-245
-        f = T(-1) / delta;
-        g = T(1000000.0);
-        return;
+    KS_FN void fg(T sigma, T& f, T& g, bool& deg) const {
+        deg = degenerate(sigma);
+        if (deg) {  // obs.py:242-245
+            f = T(-1) / delta;
+            g = T(1000000.0);
+            return;
+        }
+        T n2 = T(0), s3 = T(0);
+        KS_LOOP
+        for (int j = 0; j < m; ++j) {
+            const T D = L[j] + sigma;
+            const T p = A[j] / D;
+            n2 += p * p;
+            s3 += (A[j] * A[j]) / (D * D * D);
+        }
+        const T nrm = ks_sqrt(n2);
+        f = T(1) / nrm - T(1) / delta;
+        g = s3 / (nrm * nrm * nrm);
     }
-    T n2 = T(0), s3 = T(0);
-    for (int j = 0; j < m; ++j) {
-        T D = Lam[j] + sigma;
-        T p = a[j] / D;
-        n2 += p * p;
-        s3 += (a[j] * a[j]) / (D * D * D);
+    KS_FN T f_only(T sigma) const {
+        if (degenerate(sigma)) return T(-1) / delta;
+        T n2 = T(0);
+        KS_LOOP
+        for (int j = 0; j < m; ++j) {
+            const T p = A[j] / (L[j] + sigma);
+            n2 += p * p;
+        }
+        return T(1) / ks_sqrt(n2) - T(1) / delta;
     }
-    T nrm = ks_sqrt(n2);
-    f = T(1) / nrm - T(1) / delta;
-    g = s3 / (nrm * nrm * nrm);
+};
+
+template <class T>
+KS_BIG inline void phibar_fg(T sigma, const T* Lam, const T* a, int m, T delta, T tol, T& f, T& g, bool& deg) {
+    Secular<T> sec;
+    sec.load(Lam, a, m, delta, tol);
+    sec.fg(sigma, f, g, deg);
 }
 
 template <class T>
-KS_FN inline T phibar_f(T sigma, const T* Lam, const T* a, int m, T delta, T tol) {
-    T n2 = T(0);
-    for (int j = 0; j < m; ++j) {
-        T D = Lam[j] + sigma;
-        if (fabs(a[j]) < tol || fabs(D) < tol) return T(-1) / delta;
-    }
-    for (int j = 0; j < m; ++j) {
-        T p = a[j] / (Lam[j] + sigma);
-        n2 += p * p;
-    }
-    return T(1) / ks_sqrt(n2) - T(1) / delta;
+KS_BIG inline T phibar_f(T sigma, const T* Lam, const T* a, int m, T delta, T tol) {
+    Secular<T> sec;
+    sec.load(Lam, a, m, delta, tol);
+    return sec.f_only(sigma);
 }
 
 template <class T>
-KS_FN inline T newton(T x0, const T* Lam, const T* a, int m, T delta, T tol, int& iters, int& ndeg) {
+KS_BIG inline T newton(T x0, const T* Lam, const T* a, int m, T delta, T tol, int& iters, int& ndeg) {
+    Secular<T> sec;
+    sec.load(Lam, a, m, delta, tol);
     T x = x0, f, g;
     bool deg;
     bool adeg = false;
-    for (int j = 0; j < m; ++j) adeg = adeg || (fabs(a[j]) < tol);
+    KS_LOOP
+    for (int j = 0; j < m; ++j) adeg = adeg || (fabs(sec.A[j]) < tol);
     if (adeg) {
         // some |a_j| < tol: phibar_fg returns (-1/delta, 1/tol) for EVERY sigma (obs.py:242-245),
         // so the reference's loop is sigma <- sigma - f/g, 200 times (or not at all when
@@ -230,504 +392,445 @@ KS_FN inline T newton(T x0, const T* Lam, const T* a, int m, T delta, T tol, int
         iters = 0;
         ndeg = 1;
         const T inc = f / g;
-        if (fabs(f) > tol)
+        if (fabs(f) > tol) {
+            KS_LOOP
             for (; iters < 200; ++iters) x = x - inc;
+        }
         ndeg += iters;
         return x;
     }
-    phibar_fg<T>(x, Lam, a, m, delta, tol, f, g, deg);
+    sec.fg(x, f, g, deg);
     iters = 0;
     ndeg = deg ? 1 : 0;
+    KS_LOOP
     while (fabs(f) > tol && iters < 200) {  // obs.py:217
         x = x - f / g;
-        phibar_fg<T>(x, Lam, a, m, delta, tol, f, g, deg);
+        sec.fg(x, f, g, deg);
         ndeg += deg ? 1 : 0;
         ++iters;
     }
     return x;
 }
 
-// ---- logical (oldest..newest) views of the Gram blocks --------------------------
-struct Compact {
-    int k;
-    double gamma;
-    double SS[M * M], SY[M * M], YY[M * M];
-    double Minv[M * M];  // diag(S^T Y) + L + L^T - gamma S^T S + tol*||.||_F I   (lsr1.py:168-179)
-    double G[M * M];     // Psi^T Psi
-};
-
-// Work arrays of the k-space routines.  On the device this lives in shared memory of
-// the last CTA (keeps the per-thread stack frame of the streaming kernels small).
-struct Scratch {
-    Compact C;
-    double R[M * M], LU[M * M], MR[M * M], RMR[M * M], U[M * M], RinvU[M * M], W[M * M];
-    double D[M], b[M], x[M], y[M], q[M], wv[M], col[M];
-    int piv[M], pw[M];
-};
-
-KS_FN inline void build_compact(const dd4ml_state* st, Compact& c) {
+// ---- logical (oldest..newest) views of the Gram blocks: Minv and G = Psi^T Psi (collective) ------
+KS_BIG inline void build_compact(const dd4ml_state* st, Scratch* ws) {
     const int k = (int)st->k[0];
     const double gam = st->gamma[0];
-    c.k = k;
-    c.gamma = gam;
-    for (int i = 0; i < k; ++i) {
-        const int pi = (int)st->order[i];
-        for (int j = 0; j < k; ++j) {
-            const int pj = (int)st->order[j];
-            c.SS[i * M + j] = st->SS[pi * MS + pj];
-            c.SY[i * M + j] = st->SY[pi * MS + pj];
-            c.YY[i * M + j] = st->YY[pi * MS + pj];
-        }
-    }
+    KS_PAR2(i, j, k) {
+        const int pi = (int)st->order[i], pj = (int)st->order[j];
+        const double sy_ij = st->SY[pi * MS + pj], sy_ji = st->SY[pj * MS + pi];
+        const double ss = st->SS[pi * MS + pj], yy = st->YY[pi * MS + pj];
+        ws->Minv[i * M + j] = ((i >= j) ? sy_ij : sy_ji) - gam * ss;
+        ws->G[i * M + j] = yy - gam * (sy_ij + sy_ji) + gam * gam * ss;
+    } KS_END2
+    KS_SYNC();
+    KS_PAR(i, k) ws->Dw[i] = dots(ws->Minv + i * M, 1, ws->Minv + i * M, 1, k);   // row sums of squares
+    KS_SYNC();
     double fro = 0.0;
-    for (int i = 0; i < k; ++i)
-        for (int j = 0; j < k; ++j) {
-            double sy = (i >= j) ? c.SY[i * M + j] : c.SY[j * M + i];
-            double v = sy - gam * c.SS[i * M + j];
-            c.Minv[i * M + j] = v;
-            fro += v * v;
-            c.G[i * M + j] = c.YY[i * M + j] - gam * (c.SY[i * M + j] + c.SY[j * M + i]) + gam * gam * c.SS[i * M + j];
-        }
-    const double reg = st->tol[0] * sqrt(fro);
-    for (int i = 0; i < k; ++i) c.Minv[i * M + i] += reg;
+    KS_LOOP
+    for (int i = 0; i < k; ++i) fro += ws->Dw[i];
+    const double reg = st->tol[0] * dsqrt(fro);
+    KS_SYNC();                          // every lane has summed the unregularised matrix
+    KS_PAR(i, k) ws->Minv[i * M + i] += reg;
+    KS_SYNC();
 }
 
-KS_FN inline double dotk(const double* a, const double* b, int k) {
-    double s = 0.0;
-    for (int i = 0; i < k; ++i) s += a[i] * b[i];
-    return s;
+// out = A v for a row-major k x k block (collective: one row per lane)
+KS_FN inline void matvec(const double* A, const double* v, int k, double* out) {
+    KS_PAR(i, k) out[i] = dots(A + i * M, 1, v, 1, k);
+    KS_SYNC();
 }
-KS_FN inline double quadk(const double* A, const double* x, int k) {
-    double s = 0.0;
-    for (int i = 0; i < k; ++i)
-        for (int j = 0; j < k; ++j) s += x[i] * A[i * M + j] * x[j];
-    return s;
-}
-
-// p = cg*g + Psi*c  ->  p^T p, g^T p via the Gram identities
-struct StepK {
-    double cg;
-    double c[M];
-};
-KS_FN inline double step_pp(const Compact& C, const double* b, double gg, const StepK& s) {
-    return s.cg * s.cg * gg + 2.0 * s.cg * dotk(s.c, b, C.k) + quadk(C.G, s.c, C.k);
-}
-KS_FN inline double step_gp(const Compact& C, const double* b, double gg, const StepK& s) {
-    return s.cg * gg + dotk(s.c, b, C.k);
-}
-
-// register-resident variants for k <= KS_SMALL_MAX (kspace_small.h, included at the end of this file):
-// fully unrolled, compile-time sized; k = 5 (TR's hard-coded memory length) runs 3x faster than
-// through the generic shared-memory-scratch routines (185 k -> ~60 k cycles)
-constexpr int KS_SMALL_MAX = 5;   // (6 doubles the compile time of every kernel file for a rare memory length)
-template <class T, int K>
-KS_FN bool second_order_s(dd4ml_state* st, double gn, double gg, double delta, double& cg_out, double (&c_out)[M],
-                          double& pred, double& pp, double& gp);
-template <int K>
-KS_FN bool update_us_uu_s(dd4ml_state* st, double ss, double sy, double yy, double& us, double& uu);
 
 // =================================================================================
 // The trust-region sub-problem.  mode 0: TR (tr.py:150-176), mode 1: LSSR1_TR
 // (additionally clip to the radius and flip to a descent direction,
 // lssr1_tr.py:563-587).  Reads gg, ginf, Sg, Yg and the L-SR1 blocks from the
-// state; writes the step descriptor (cg, cS, cY) and the report fields.
+// state; writes the step descriptor (cg, cS, cY) and the report fields.  Collective.
+// Every step is p = cg g + lam Psi wv, so p^T p, g^T p and p^T B p are quadratic forms in
+// (cg, lam) with coefficients g^T g, wv^T Psi^T g, wv^T G wv, ... computed once.
 // =================================================================================
-template <class T>
-KS_FN inline void tr_solve(dd4ml_state* st, int mode, Scratch* ws) {
+KS_BIG inline double newton_rt(bool f32, double x0, Scratch* ws, int m, double delta, double tol, int& it, int& nd) {
+    if (f32) return (double)newton<float>((float)x0, ws->Lf, ws->Af, m, (float)delta, (float)tol, it, nd);
+    return newton<double>(x0, ws->Ld, ws->Ad, m, delta, tol, it, nd);
+}
+KS_BIG inline double phibar_f_rt(bool f32, double sigma, Scratch* ws, int m, double delta, double tol) {
+    if (f32) return (double)phibar_f<float>((float)sigma, ws->Lf, ws->Af, m, (float)delta, (float)tol);
+    return phibar_f<double>(sigma, ws->Ld, ws->Ad, m, delta, tol);
+}
+
+// `f32`: the reference's working dtype T is float32 (else float64).  Quantities that are T values in the
+// reference are held as doubles that are exactly representable in T (rT after every T operation).
+KS_BIG inline void tr_solve(dd4ml_state* st, int mode, bool f32, Scratch* ws) {
     const double delta = st->delta[0], tol = st->tol[0], gg = st->gg[0];
     const int k = (st->second_order[0] != 0.0) ? (int)st->k[0] : 0;
     const double c_s0 = KS_CLOCK();
-    st->cyc_eigh[0] = st->cyc_newton[0] = st->jacobi_sweeps[0] = 0.0;
-    for (int i = 0; i < MS; ++i) { st->cS[i] = 0.0; st->cY[i] = 0.0; }
-    st->cg[0] = 0.0;
-    st->err[0] = DD4ML_ERR_NONE;
-    st->sigma[0] = st->sigma0[0] = st->tau[0] = 0.0;
-    st->newton_iters[0] = st->newton_deg[0] = 0.0;
-    st->dogleg_branch[0] = 0.0;
-    st->flip[0] = 0.0;
-    st->clip_scale[0] = 1.0;
-    st->lam_min[0] = st->gBg[0] = 0.0;
-    st->converged[0] = 0.0;
-    st->solve_valid[0] = 1.0;
-
-    const T gnT = (T)((st->norm_inf[0] != 0.0) ? st->ginf[0] : sqrt(gg));
-    const double gn = (double)gnT;
-    st->gn[0] = gn;
+    const double gn = rT((st->norm_inf[0] != 0.0) ? st->ginf[0] : dsqrt(gg), f32);   // gnT
+    const double gam = st->gamma[0];
+    KS_SYNC();                          // all lanes hold the inputs before the master resets the report
+    KS_PAR(i, MS) { st->cS[i] = 0.0; st->cY[i] = 0.0; }
+    KS_MASTER {
+        st->cyc_eigh[0] = st->cyc_newton[0] = st->jacobi_sweeps[0] = 0.0;
+        st->cg[0] = 0.0;
+        st->err[0] = DD4ML_ERR_NONE;
+        st->sigma[0] = st->sigma0[0] = st->tau[0] = 0.0;
+        st->newton_iters[0] = st->newton_deg[0] = 0.0;
+        st->dogleg_branch[0] = 0.0;
+        st->flip[0] = 0.0;
+        st->clip_scale[0] = 1.0;
+        st->lam_min[0] = st->gBg[0] = 0.0;
+        st->converged[0] = 0.0;
+        st->solve_valid[0] = 1.0;
+        st->gn[0] = gn;
+    }
     if (gn <= tol) {  // tr.py:147 / lssr1_tr.py:509
-        st->converged[0] = 1.0;
-        st->pred[0] = st->pnorm[0] = st->gp[0] = st->psq[0] = st->dphi0[0] = 0.0;
-        st->case_id[0] = DD4ML_CASE_FIRST_ORDER;
+        KS_MASTER {
+            st->converged[0] = 1.0;
+            st->pred[0] = st->pnorm[0] = st->gp[0] = st->psq[0] = st->dphi0[0] = 0.0;
+            st->case_id[0] = DD4ML_CASE_FIRST_ORDER;
+        }
+        KS_SYNC();
         return;
     }
+#define KS_FAIL(code) { KS_MASTER { st->err[0] = (code); st->solve_valid[0] = 0.0; } KS_SYNC(); return; }
 
-    double pred, pp, gp;
-    Compact& C = ws->C;
-    C.k = 0;
-    double* b = ws->b;
-    StepK S;
-    for (int i = 0; i < M; ++i) S.c[i] = 0.0;
-
+    double pred, pp, gp, cg, lam = 0.0;   // the step: p = cg g + lam Psi wv
     if (k == 0) {  // optimizer_utils.py:197-215
-        const T scale = (T(1) / gnT) * (T)delta;  // python: delta / gn  ==  gn.reciprocal() * delta
-        S.cg = -(double)scale;
-        pred = (double)((T)delta * gnT);
-        pp = S.cg * S.cg * gg;
-        gp = S.cg * gg;
-        st->case_id[0] = DD4ML_CASE_FIRST_ORDER;
-    } else if (k <= KS_SMALL_MAX) {
-        bool ok;
-        switch (k) {
-            case 1: ok = second_order_s<T, 1>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
-            case 2: ok = second_order_s<T, 2>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
-            case 3: ok = second_order_s<T, 3>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
-            case 4: ok = second_order_s<T, 4>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
-            default: ok = second_order_s<T, 5>(st, gn, gg, delta, S.cg, S.c, pred, pp, gp); break;
-        }
-        if (!ok) { st->solve_valid[0] = 0.0; return; }
-        C.k = k;
-        C.gamma = st->gamma[0];
+        const double delT = rT(delta, f32);
+        const double scale = rT(rT(ddiv(1.0, gn), f32) * delT, f32);  // python: delta / gn  ==  gn.reciprocal() * delta
+        cg = -scale;
+        pred = rT(delT * gn, f32);
+        pp = cg * cg * gg;
+        gp = cg * gg;
+        KS_MASTER st->case_id[0] = DD4ML_CASE_FIRST_ORDER;
     } else {
-        build_compact(st, C);
-        const double gam = C.gamma;
+        build_compact(st, ws);
+        double* b = ws->b;
+        KS_PAR(i, k) { const int pi = (int)st->order[i]; b[i] = st->Yg[pi] - gam * st->Sg[pi]; }  // Psi^T g
+        KS_SYNC();
         bool ok = finite(gg) && finite(delta) && finite(gam);
+        KS_LOOP
         for (int i = 0; i < k; ++i) {
-            const int pi = (int)st->order[i];
-            b[i] = st->Yg[pi] - gam * st->Sg[pi];  // Psi^T g
             ok = ok && finite(b[i]);
-            for (int j = 0; j < k; ++j) ok = ok && finite(C.G[i * M + j]) && finite(C.Minv[i * M + j]);
+            KS_LOOP
+            for (int j = 0; j < k; ++j) ok = ok && finite(ws->G[i * M + j]) && finite(ws->Minv[i * M + j]);
         }
-        if (!ok) { st->err[0] = DD4ML_ERR_NONFINITE; st->solve_valid[0] = 0.0; return; }
-        if (delta < 0) { st->err[0] = DD4ML_ERR_NEG_DELTA; st->solve_valid[0] = 0.0; return; }
+        if (!ok) KS_FAIL(DD4ML_ERR_NONFINITE)
+        if (delta < 0) KS_FAIL(DD4ML_ERR_NEG_DELTA)
 
         // ---- OBS (obs.py:61-95) ----
         double *R = ws->R, *LU = ws->LU, *MR = ws->MR, *RMR = ws->RMR, *U = ws->U, *D = ws->D, *RinvU = ws->RinvU;
-        int* piv = ws->piv;
-        if (!chol_upper(C.G, k, R)) { st->err[0] = DD4ML_ERR_CHOLESKY; st->solve_valid[0] = 0.0; return; }
-        for (int i = 0; i < k * M; ++i) LU[i] = C.Minv[i];
-        if (!lu_factor(LU, k, piv)) { st->err[0] = DD4ML_ERR_SINGULAR; st->solve_valid[0] = 0.0; return; }
-        for (int c = 0; c < k; ++c) {  // MR[:, c] = Minv \ R^T[:, c]
-            double* col = ws->col;
-            for (int r = 0; r < k; ++r) col[r] = R[c * M + r];
-            lu_solve(LU, piv, k, col);
-            for (int r = 0; r < k; ++r) MR[r * M + c] = col[r];
-        }
-        for (int i = 0; i < k; ++i)
-            for (int j = 0; j < k; ++j) {
-                double s = 0.0;
-                for (int r = 0; r < k; ++r) s += R[i * M + r] * MR[r * M + j];
-                RMR[i * M + j] = s;
-            }
-        for (int i = 0; i < k; ++i)
-            for (int j = i + 1; j < k; ++j) {
-                double s = 0.5 * (RMR[i * M + j] + RMR[j * M + i]);
+        if (!chol_upper(ws->G, k, R)) KS_FAIL(DD4ML_ERR_CHOLESKY)
+        KS_PAR2(i, j, k) {
+            LU[i * M + j] = ws->Minv[i * M + j];
+            MR[i * M + j] = R[j * M + i];          // right-hand sides R^T
+        } KS_END2
+        KS_SYNC();
+        if (!lu_factor(LU, k, ws->piv)) KS_FAIL(DD4ML_ERR_SINGULAR)
+        lu_solve_cols(LU, ws->piv, k, MR, M, k);    // MR = Minv \ R^T
+        KS_PAR2(i, j, k) { RMR[i * M + j] = dots(R + i * M, 1, MR + j, M, k); } KS_END2
+        KS_SYNC();
+        KS_PAR2(i, j, k) {
+            if (i < j) {
+                const double s = 0.5 * (RMR[i * M + j] + RMR[j * M + i]);
                 RMR[i * M + j] = RMR[j * M + i] = s;
             }
+        } KS_END2
+        KS_SYNC();
         const double c_e0 = KS_CLOCK();
-        st->jacobi_sweeps[0] = jacobi_eigh(RMR, k, D, U);
-        st->cyc_eigh[0] = KS_CLOCK() - c_e0;
-        T Lam[M + 1], a[M + 1];
-        const T tolT = (T)OBS_TOL, gamT = (T)gam, delT = (T)delta;
-        for (int i = 0; i < k; ++i) Lam[i] = (T)D[i] + gamT;
-        Lam[k] = gamT;
-        for (int i = 0; i <= k; ++i)
-            if (fabs(Lam[i]) < tolT) Lam[i] = T(0);
-        const T lam_min = (Lam[0] < gamT) ? Lam[0] : gamT;
-        st->lam_min[0] = (double)lam_min;
-        for (int c = 0; c < k; ++c) {  // RinvU[:, c] = R \ U[:, c]
+        const int sweeps = jacobi_eigh(RMR, k, D, U, ws);
+        KS_MASTER { st->jacobi_sweeps[0] = sweeps; st->cyc_eigh[0] = KS_CLOCK() - c_e0; }
+        double* Lam = ws->Ld;               // Lambda, a as T values held in doubles (+ float copies for T = float)
+        double* a = ws->Ad;
+        const double tolT = rT(OBS_TOL, f32), gamT = rT(gam, f32), delT = rT(delta, f32);
+        KS_PAR(c, k) {  // RinvU[:, c] = R \ U[:, c];  a_c = (R^{-1} U)[:, c] . Psi^T g
+            KS_LOOP
             for (int r = k - 1; r >= 0; --r) {
                 double s = U[r * M + c];
+                KS_LOOP
                 for (int j = r + 1; j < k; ++j) s -= R[r * M + j] * RinvU[j * M + c];
-                RinvU[r * M + c] = s / R[r * M + r];
+                RinvU[r * M + c] = ddiv(s, R[r * M + r]);
             }
+            const double s = dots(RinvU + c, M, b, 1, k);
+            ws->ad[c] = s;
+            a[c] = rT(s, f32);
+            double L = rT(rT(D[c], f32) + gamT, f32);
+            if (fabs(L) < tolT) L = 0.0;
+            Lam[c] = L;
+            ws->Af[c] = (float)a[c];
+            ws->Lf[c] = (float)L;
         }
-        double gpgp = 0.0;
-        for (int i = 0; i < k; ++i) {
-            double s = 0.0;
-            for (int r = 0; r < k; ++r) s += RinvU[r * M + i] * b[r];
-            a[i] = (T)s;
-            gpgp += s * s;
-        }
-        {
-            double d = gg - gpgp;
-            a[k] = (T)sqrt(d > 0.0 ? d : 0.0);
-        }
-        T tauT;
-        T h2 = T(0);
-        for (int i = 0; i <= k; ++i) { T h = a[i] / Lam[i]; h2 += h * h; }
-        if (lam_min > T(0) && ks_sqrt(h2) <= delT) {  // case A, obs.py:97
+        KS_SYNC();
+        const double gpgp = dotk(ws->ad, ws->ad, k);
+        const double dd = gg - gpgp;
+        const double a_last = rT(dsqrt(dd > 0.0 ? dd : 0.0), f32);
+        const double lam_last = (fabs(gamT) < tolT) ? 0.0 : gamT;
+        KS_MASTER { a[k] = a_last; Lam[k] = lam_last; ws->Af[k] = (float)a_last; ws->Lf[k] = (float)lam_last; }
+        KS_SYNC();
+        const double lam_min = (Lam[0] < gamT) ? Lam[0] : gamT;
+        KS_MASTER st->lam_min[0] = lam_min;
+        double tauT;
+        double h2 = 0.0;
+        KS_LOOP
+        for (int i = 0; i <= k; ++i) { const double h = rT(ddiv(a[i], Lam[i]), f32); h2 = rT(h2 + rT(h * h, f32), f32); }
+        if (lam_min > 0.0 && rT(dsqrt(h2), f32) <= delT) {  // case A, obs.py:97
             tauT = gamT;
-            st->case_id[0] = DD4ML_CASE_A;
+            KS_MASTER st->case_id[0] = DD4ML_CASE_A;
         } else {
-            if (lam_min <= T(0) && phibar_f<T>(-lam_min, Lam, a, k + 1, delT, tolT) >= T(0)) {
-                st->err[0] = DD4ML_ERR_HARD_CASE;  // obs.py:100-158, unreachable for gamma > 0
-                st->solve_valid[0] = 0.0;
-                return;
-            }
-            T x0 = T(0);
-            if (!(lam_min > T(0))) {  // obs.py:162-168
-                T sh = a[0] / delT - Lam[0];
-                for (int i = 1; i <= k; ++i) { T v = a[i] / delT - Lam[i]; if (v > sh) sh = v; }
+            if (lam_min <= 0.0 && phibar_f_rt(f32, -lam_min, ws, k + 1, delT, tolT) >= 0.0)
+                KS_FAIL(DD4ML_ERR_HARD_CASE)   // obs.py:100-158, unreachable for gamma > 0
+            double x0 = 0.0;
+            if (!(lam_min > 0.0)) {  // obs.py:162-168
+                double sh = rT(rT(ddiv(a[0], delT), f32) - Lam[0], f32);
+                KS_LOOP
+                for (int i = 1; i <= k; ++i) { const double v = rT(rT(ddiv(a[i], delT), f32) - Lam[i], f32); if (v > sh) sh = v; }
                 x0 = (sh > -lam_min) ? sh : -lam_min;
             }
             int it, nd;
             const double c_n0 = KS_CLOCK();
-            T sig = newton<T>(x0, Lam, a, k + 1, delT, tolT, it, nd);
-            st->cyc_newton[0] = KS_CLOCK() - c_n0;
-            if (!finite((double)sig)) sig = newton<T>(T(0), Lam, a, k + 1, delT, tolT, it, nd);
-            st->sigma0[0] = (double)x0;
-            st->sigma[0] = (double)sig;
-            st->newton_iters[0] = it;
-            st->newton_deg[0] = nd;
-            st->case_id[0] = DD4ML_CASE_C;
-            tauT = gamT + sig;
+            double sig = newton_rt(f32, x0, ws, k + 1, delT, tolT, it, nd);
+            if (!finite(sig)) sig = newton_rt(f32, 0.0, ws, k + 1, delT, tolT, it, nd);
+            KS_MASTER {
+                st->cyc_newton[0] = KS_CLOCK() - c_n0;
+                st->sigma0[0] = x0;
+                st->sigma[0] = sig;
+                st->newton_iters[0] = it;
+                st->newton_deg[0] = nd;
+                st->case_id[0] = DD4ML_CASE_C;
+            }
+            tauT = rT(gamT + sig, f32);
         }
-        const double tau = (double)tauT;
-        st->tau[0] = tau;
-        // SMW step exactly as coded (obs.py:175-182): p = -g/tau + Psi (tau Minv + G)^{-1} Psi^T g
-        double *W = ws->W, *wv = ws->wv;
-        for (int i = 0; i < k * M; ++i) W[i] = tau * C.Minv[i] + C.G[i];
-        int* pw = ws->pw;
-        if (!lu_factor(W, k, pw)) { st->err[0] = DD4ML_ERR_SINGULAR; st->solve_valid[0] = 0.0; return; }
-        for (int i = 0; i < k; ++i) wv[i] = b[i];
-        lu_solve(W, pw, k, wv);
-        StepK Pb;
-        Pb.cg = (double)(T(-1) / tauT);
-        for (int i = 0; i < M; ++i) Pb.c[i] = (i < k) ? wv[i] : 0.0;
-
+        const double tau = tauT;
+        KS_MASTER st->tau[0] = tau;
+        // SMW step exactly as coded (obs.py:175-182): p_b = -g/tau + Psi (tau Minv + G)^{-1} Psi^T g
+        double *W = ws->W, *wv = ws->wv, *x = ws->x, *z = ws->z, *Gw = ws->Gw;
+        KS_PAR2(i, j, k) { W[i * M + j] = tau * ws->Minv[i * M + j] + ws->G[i * M + j]; } KS_END2
+        KS_PAR(i, k) { wv[i] = b[i]; x[i] = b[i]; }
+        KS_SYNC();
+        if (!lu_factor(W, k, ws->pw)) KS_FAIL(DD4ML_ERR_SINGULAR)
+        KS_PAR(c, 2) {
+            if (c == 0) lu_solve_vec(W, ws->pw, k, wv, 1);     // wv = (tau Minv + G) \ Psi^T g
+            else lu_solve_vec(LU, ws->piv, k, x, 1);           // x  = Minv \ Psi^T g
+        }
+        KS_SYNC();
+        matvec(ws->G, wv, k, Gw);
+        KS_PAR(i, k) z[i] = Gw[i];
+        KS_SYNC();
+        lu_solve_cols(LU, ws->piv, k, z, 1, 1);     // z  = Minv \ (G wv)
+        const double bx = dotk(b, x, k), bw = dotk(b, wv, k), wGw = dotk(wv, Gw, k);
+        const double bz = dotk(b, z, k), gwx = dotk(Gw, x, k), gwz = dotk(Gw, z, k);
+        const double cgb = rT(ddiv(-1.0, tauT), f32);
+#define KS_PP(c_, l_) ((c_) * (c_) * gg + 2.0 * (c_) * (l_) * bw + (l_) * (l_) * wGw)
+#define KS_GP(c_, l_) ((c_) * gg + (l_) * bw)
         // ---- Cauchy point and dogleg (optimizer_utils.py:259-296) ----
-        double* x = ws->x;
-        for (int i = 0; i < k; ++i) x[i] = b[i];
-        lu_solve(LU, piv, k, x);
-        const double gBg = gam * gg + dotk(b, x, k);
-        st->gBg[0] = gBg;
-        S = Pb;
+        const double gBg = gam * gg + bx;
+        KS_MASTER st->gBg[0] = gBg;
+        cg = cgb;
+        lam = 1.0;
+        double branch = 0.0;
         if (st->dogleg[0] != 0.0 && gBg > 0.0) {
-            const double alpha = gn * gn / gBg;
-            const double cc = (alpha * sqrt(gg) >= delta) ? -(delta / gn) : -alpha;
-            const double pb_norm = sqrt(step_pp(C, b, gg, Pb));
-            const double pc_norm = fabs(cc) * sqrt(gg);
+            const double alpha = ddiv(gn * gn, gBg);
+            const double cc = (alpha * dsqrt(gg) >= delta) ? -ddiv(delta, gn) : -alpha;
+            const double pb_norm = dsqrt(KS_PP(cgb, 1.0));
+            const double pc_norm = fabs(cc) * dsqrt(gg);
             if (pb_norm <= delta) {
-                st->dogleg_branch[0] = 1.0;
+                branch = 1.0;
             } else if (pc_norm >= delta) {
-                S.cg = cc;
-                for (int i = 0; i < k; ++i) S.c[i] = 0.0;
-                st->dogleg_branch[0] = 2.0;
+                cg = cc; lam = 0.0; branch = 2.0;
             } else {
-                StepK d = Pb;
-                d.cg = Pb.cg - cc;
-                const double qa = step_pp(C, b, gg, d);
-                const double qb = 2.0 * cc * step_gp(C, b, gg, d);
+                const double dcg = cgb - cc;                   // d = p_b - p_c = dcg g + Psi wv
+                const double qa = KS_PP(dcg, 1.0);
+                const double qb = 2.0 * cc * KS_GP(dcg, 1.0);
                 const double qc = cc * cc * gg - delta * delta;
                 const double disc = qb * qb - 4.0 * qa * qc;
                 if (disc < 0.0) {
-                    S.cg = cc;
-                    for (int i = 0; i < k; ++i) S.c[i] = 0.0;
-                    st->dogleg_branch[0] = 3.0;
+                    cg = cc; lam = 0.0; branch = 3.0;
                 } else {
-                    const double t = (-qb + sqrt(disc)) / (2.0 * qa);
-                    S.cg = cc + t * d.cg;
-                    for (int i = 0; i < k; ++i) S.c[i] = t * d.c[i];
-                    st->dogleg_branch[0] = 4.0;
+                    const double t = ddiv(-qb + dsqrt(disc), 2.0 * qa);
+                    cg = cc + t * dcg; lam = t; branch = 4.0;
                 }
             }
         }
+        KS_MASTER st->dogleg_branch[0] = branch;
         // ---- predicted reduction -(g^T p + 1/2 p^T B p) (optimizer_utils.py:298-305) ----
-        pp = step_pp(C, b, gg, S);
-        gp = step_gp(C, b, gg, S);
-        double *q = ws->q, *y = ws->y;
-        for (int i = 0; i < k; ++i) {
-            double s = S.cg * b[i];
-            for (int j = 0; j < k; ++j) s += C.G[i * M + j] * S.c[j];
-            q[i] = s;
-        }
-        for (int i = 0; i < k; ++i) y[i] = q[i];
-        lu_solve(LU, piv, k, y);
-        const double pBp = gam * pp + dotk(q, y, k);
-        pred = -(gp + 0.5 * pBp);
+        // Psi^T p = q = cg b + lam G wv,  B p = gamma p + Psi Minv^{-1} q,  Minv^{-1} q = cg x + lam z
+        pp = KS_PP(cg, lam);
+        gp = KS_GP(cg, lam);
+        const double qy = cg * cg * bx + cg * lam * (bz + gwx) + lam * lam * gwz;
+        pred = -(gp + 0.5 * (gam * pp + qy));
+#undef KS_PP
+#undef KS_GP
     }
 
     if (mode == 1) {  // lssr1_tr.py:563-587 (the momentum term is identically zero)
         if (pp > tol) {
-            const double nrm = sqrt((double)(T)pp);
-            const double sc = (delta / nrm < 1.0) ? delta / nrm : 1.0;
-            S.cg *= sc;
-            for (int i = 0; i < C.k; ++i) S.c[i] *= sc;
+            const double nrm = dsqrt(rT(pp, f32));
+            const double q = ddiv(delta, nrm);
+            const double sc = (q < 1.0) ? q : 1.0;
+            cg *= sc;
+            lam *= sc;
             pp *= sc * sc;
             gp *= sc;
-            st->clip_scale[0] = sc;
+            KS_MASTER st->clip_scale[0] = sc;
         }
         if (gp > 0.0) {
-            S.cg = -S.cg;
-            for (int i = 0; i < C.k; ++i) S.c[i] = -S.c[i];
+            cg = -cg;
+            lam = -lam;
             pred = -pred;
             gp = -gp;
-            st->flip[0] = 1.0;
+            KS_MASTER st->flip[0] = 1.0;
         }
     }
-    st->cg[0] = S.cg;
-    for (int i = 0; i < C.k; ++i) {
+    KS_PAR(i, k) {
         const int pi = (int)st->order[i];
-        st->cY[pi] = S.c[i];
-        st->cS[pi] = -C.gamma * S.c[i];
+        const double c = lam * ws->wv[i];
+        st->cY[pi] = c;
+        st->cS[pi] = -gam * c;
     }
-    st->pred[0] = pred;
-    st->psq[0] = pp;
-    st->pnorm[0] = sqrt(pp > 0.0 ? pp : 0.0);
-    st->gp[0] = gp;
-    st->dphi0[0] = gp;
-    st->cyc_solve[0] = KS_CLOCK() - c_s0;
+    KS_MASTER {
+        st->cg[0] = cg;
+        st->pred[0] = pred;
+        st->psq[0] = pp;
+        st->pnorm[0] = dsqrt(pp > 0.0 ? pp : 0.0);
+        st->gp[0] = gp;
+        st->dphi0[0] = gp;
+        st->cyc_solve[0] = KS_CLOCK() - c_s0;
+    }
+    KS_SYNC();
+#undef KS_FAIL
 }
+// typed wrapper (tests/hostshim, readability)
+template <class T>
+KS_FN inline void tr_solve(dd4ml_state* st, int mode, Scratch* ws) { tr_solve(st, mode, sizeof(T) == 4, ws); }
 
 // =================================================================================
 // LSR1.update_memory acceptance chain (lsr1.py:66-144) on the candidate pair whose
 // reductions sit in c_ss, c_sy, c_yy, c_Ss, c_Ys, c_Sy, c_Yy (PHYSICAL slot index)
 // and whose vectors were written to the spare slot.  On acceptance the spare slot
 // joins the ring (dropping the oldest pair at capacity), the Gram blocks grow by one
-// row/column and gamma <- max(y^T y / y^T s, tol).
+// row/column and gamma <- max(y^T y / y^T s, tol).  Collective; the result is uniform.
 // =================================================================================
-KS_FN inline bool lsr1_try_update(dd4ml_state* st, Scratch* ws) {
+KS_BIG inline bool lsr1_try_update(dd4ml_state* st, Scratch* ws) {
     const double tol = st->tol[0];
     const double ss = st->c_ss[0], sy = st->c_sy[0], yy = st->c_yy[0];
     const int k = (int)st->k[0], m = (int)st->mem_len[0];
     const double gam = st->gamma[0];
-    st->pair_ok[0] = 0.0;
-    const double sn = sqrt(ss), yn = sqrt(yy);
+    const int ns = (int)st->spare[0];
+    const int oldest = (int)st->order[0];
+    KS_SYNC();
+    KS_MASTER st->pair_ok[0] = 0.0;
+    const double sn = dsqrt(ss), yn = dsqrt(yy);
     if (!(sn > tol) || !(yn > tol)) return false;        // :72
     if (!(fabs(sy) > tol * (sn * yn))) return false;     // :78
     double us, uu;
     if (k == 0) {  // B = gamma I
         us = sy - gam * ss;
         uu = yy - 2.0 * gam * sy + gam * gam * ss;
-    } else if (k <= KS_SMALL_MAX) {
-        bool ok;
-        switch (k) {
-            case 1: ok = update_us_uu_s<1>(st, ss, sy, yy, us, uu); break;
-            case 2: ok = update_us_uu_s<2>(st, ss, sy, yy, us, uu); break;
-            case 3: ok = update_us_uu_s<3>(st, ss, sy, yy, us, uu); break;
-            case 4: ok = update_us_uu_s<4>(st, ss, sy, yy, us, uu); break;
-            default: ok = update_us_uu_s<5>(st, ss, sy, yy, us, uu); break;
-        }
-        if (!ok) return false;
     } else {
-        Compact& C = ws->C;
-        build_compact(st, C);
-        double *bs = ws->b, *by = ws->y, *x = ws->x, *LU = ws->LU;
-        int* piv = ws->piv;
-        for (int i = 0; i < k; ++i) {
+        build_compact(st, ws);
+        double *bs = ws->bs, *by = ws->by, *x = ws->x, *LU = ws->LU, *Gx = ws->Gw;
+        KS_PAR(i, k) {
             const int pi = (int)st->order[i];
             bs[i] = st->c_Ys[pi] - gam * st->c_Ss[pi];   // Psi^T s
             by[i] = st->c_Yy[pi] - gam * st->c_Sy[pi];   // Psi^T y
             x[i] = bs[i];
         }
-        for (int i = 0; i < k * M; ++i) LU[i] = C.Minv[i];
-        if (!lu_factor(LU, k, piv)) { st->err[0] = DD4ML_ERR_SINGULAR; return false; }
-        lu_solve(LU, piv, k, x);                         // x = Minv \ Psi^T s
-        us = sy - gam * ss - dotk(bs, x, k);
-        uu = yy + gam * gam * ss + quadk(C.G, x, k) - 2.0 * gam * sy - 2.0 * dotk(by, x, k)
-             + 2.0 * gam * dotk(bs, x, k);
+        KS_PAR2(i, j, k) { LU[i * M + j] = ws->Minv[i * M + j]; } KS_END2
+        KS_SYNC();
+        if (!lu_factor(LU, k, ws->piv)) { KS_MASTER st->err[0] = DD4ML_ERR_SINGULAR; KS_SYNC(); return false; }
+        lu_solve_cols(LU, ws->piv, k, x, 1, 1);          // x = Minv \ Psi^T s
+        matvec(ws->G, x, k, Gx);
+        const double bsx = dotk(bs, x, k);
+        us = sy - gam * ss - bsx;
+        uu = yy + gam * gam * ss + dotk(x, Gx, k) - 2.0 * gam * sy - 2.0 * dotk(by, x, k) + 2.0 * gam * bsx;
     }
-    const double un = sqrt(uu > 0.0 ? uu : 0.0);
+    const double un = dsqrt(uu > 0.0 ? uu : 0.0);
     if (!(fabs(us) > tol * sn * un)) return false;       // :86
-    double gc = yy / sy;
+    double gc = ddiv(yy, sy);
     if (gc < tol) gc = tol;                              // :90
     const double pc2 = yy - 2.0 * gc * sy + gc * gc * ss;
-    if (!(sqrt(pc2 > 0.0 ? pc2 : 0.0) > tol * yn)) return false;  // :93
+    if (!(dsqrt(pc2 > 0.0 ? pc2 : 0.0) > tol * yn)) return false;  // :93
     // ---- accept ----
-    const int ns = (int)st->spare[0];
-    int newspare;
-    int kk = k;
+    int kk = k, newspare;
     if (k >= m) {  // drop the oldest pair; its slot becomes the spare
-        newspare = (int)st->order[0];
-        for (int i = 0; i + 1 < k; ++i) st->order[i] = st->order[i + 1];
-        st->order[k - 1] = ns;
+        newspare = oldest;
     } else {
-        st->order[k] = ns;
         kk = k + 1;
-        // first unused physical slot
-        bool used[MS];
-        for (int i = 0; i < MS; ++i) used[i] = false;
-        for (int i = 0; i < kk; ++i) used[(int)st->order[i]] = true;
+        unsigned used = 1u << ns;       // first unused physical slot
+        KS_LOOP
+        for (int i = 0; i < k; ++i) used |= 1u << (int)st->order[i];
         newspare = 0;
-        while (newspare < MS && used[newspare]) ++newspare;
+        KS_LOOP
+        while (newspare < MS && ((used >> newspare) & 1u)) ++newspare;
     }
-    for (int i = 0; i < kk; ++i) {
+    KS_SYNC();                          // every lane has read the old ring before it changes
+    KS_PAR(i, k) {                      // Gram rows/columns of the new pair against the live pairs
         const int pj = (int)st->order[i];
-        if (pj == ns) continue;
-        st->SS[ns * MS + pj] = st->SS[pj * MS + ns] = st->c_Ss[pj];
-        st->YY[ns * MS + pj] = st->YY[pj * MS + ns] = st->c_Yy[pj];
-        st->SY[pj * MS + ns] = st->c_Sy[pj];  // S_j^T y
-        st->SY[ns * MS + pj] = st->c_Ys[pj];  // s^T Y_j
+        if (!(k >= m && i == 0)) {      // (the dropped pair's entries are dead)
+            st->SS[ns * MS + pj] = st->SS[pj * MS + ns] = st->c_Ss[pj];
+            st->YY[ns * MS + pj] = st->YY[pj * MS + ns] = st->c_Yy[pj];
+            st->SY[pj * MS + ns] = st->c_Sy[pj];  // S_j^T y
+            st->SY[ns * MS + pj] = st->c_Ys[pj];  // s^T Y_j
+        }
     }
-    st->SS[ns * MS + ns] = ss;
-    st->SY[ns * MS + ns] = sy;
-    st->YY[ns * MS + ns] = yy;
-    st->k[0] = kk;
-    st->spare[0] = newspare;
-    st->gamma[0] = gc;
-    st->gen[0] += 1.0;
-    st->pair_ok[0] = 1.0;
+    KS_SYNC();
+    KS_MASTER {
+        if (k >= m) {
+            KS_LOOP
+            for (int i = 0; i + 1 < k; ++i) st->order[i] = st->order[i + 1];
+            st->order[k - 1] = ns;
+        } else {
+            st->order[k] = ns;
+        }
+        st->SS[ns * MS + ns] = ss;
+        st->SY[ns * MS + ns] = sy;
+        st->YY[ns * MS + ns] = yy;
+        st->k[0] = kk;
+        st->spare[0] = newspare;
+        st->gamma[0] = gc;
+        st->gen[0] += 1.0;
+        st->pair_ok[0] = 1.0;
+    }
+    KS_SYNC();
     return true;
 }
 
 // LSR1.B (lsr1.py:181-198): out = gamma v + Psi (Minv \ Psi^T v), expressed as the
-// coefficients (cg, cS, cY) of the output pass.  S^T v, Y^T v are read from Sg, Yg.
-KS_FN inline void lsr1_B_coefs(dd4ml_state* st, Scratch* ws) {
-    const int k = (int)st->k[0];
-    const double gam = st->gamma[0];
-    for (int i = 0; i < MS; ++i) { st->cS[i] = 0.0; st->cY[i] = 0.0; }
-    st->cg[0] = gam;
-    st->converged[0] = 0.0;
-    st->solve_valid[0] = 0.0;
-    st->err[0] = DD4ML_ERR_NONE;
-    if (k == 0) return;
-    Compact& C = ws->C;
-    build_compact(st, C);
-    double* x = ws->x;
-    for (int i = 0; i < k; ++i) {
-        const int pi = (int)st->order[i];
-        x[i] = st->Yg[pi] - gam * st->Sg[pi];
-    }
-    for (int i = 0; i < k * M; ++i) ws->LU[i] = C.Minv[i];
-    if (!lu_factor(ws->LU, k, ws->piv)) { st->err[0] = DD4ML_ERR_SINGULAR; return; }
-    lu_solve(ws->LU, ws->piv, k, x);
-    for (int i = 0; i < k; ++i) {
-        const int pi = (int)st->order[i];
-        st->cY[pi] = x[i];
-        st->cS[pi] = -gam * x[i];
-    }
-}
-
-// OBS.ComputeSBySMW (obs.py:175-182) for a caller-supplied tau (read from st->tau):
-// p = -g/tau + Psi ((tau Minv + Psi^T Psi) \ Psi^T g), as coefficients of the output pass
-// (as coded in the reference, i.e. without the paper's 1/tau on the Psi term).
-KS_FN inline void smw_coefs(dd4ml_state* st, Scratch* ws) {
+// coefficients (cg, cS, cY) of the output pass.  S^T v, Y^T v are read from Sg, Yg.  Collective.
+// With tau > 0 (OBS.ComputeSBySMW, obs.py:175-182, tau read from st->tau): p = -g/tau +
+// Psi ((tau Minv + Psi^T Psi) \ Psi^T g), as coded in the reference (no 1/tau on the Psi term).
+KS_BIG inline void coefs_B_or_smw(dd4ml_state* st, Scratch* ws, bool smw) {
     const int k = (int)st->k[0];
     const double gam = st->gamma[0], tau = st->tau[0];
-    for (int i = 0; i < MS; ++i) { st->cS[i] = 0.0; st->cY[i] = 0.0; }
-    st->cg[0] = -1.0 / tau;
-    st->converged[0] = 0.0;
-    st->solve_valid[0] = 0.0;
-    st->err[0] = DD4ML_ERR_NONE;
-    if (k == 0) return;
-    Compact& C = ws->C;
-    build_compact(st, C);
-    double* x = ws->x;
-    for (int i = 0; i < k; ++i) {
-        const int pi = (int)st->order[i];
-        x[i] = st->Yg[pi] - gam * st->Sg[pi];
+    KS_SYNC();
+    KS_PAR(i, MS) { st->cS[i] = 0.0; st->cY[i] = 0.0; }
+    KS_MASTER {
+        st->cg[0] = smw ? -1.0 / tau : gam;
+        st->converged[0] = 0.0;
+        st->solve_valid[0] = 0.0;
+        st->err[0] = DD4ML_ERR_NONE;
     }
-    for (int i = 0; i < k; ++i)
-        for (int j = 0; j < k; ++j) ws->W[i * M + j] = tau * C.Minv[i * M + j] + C.G[i * M + j];
-    if (!lu_factor(ws->W, k, ws->pw)) { st->err[0] = DD4ML_ERR_SINGULAR; return; }
-    lu_solve(ws->W, ws->pw, k, x);
-    for (int i = 0; i < k; ++i) {
+    KS_SYNC();
+    if (k == 0) return;
+    build_compact(st, ws);
+    double *x = ws->x, *A = ws->W;
+    KS_PAR(i, k) { const int pi = (int)st->order[i]; x[i] = st->Yg[pi] - gam * st->Sg[pi]; }
+    KS_PAR2(i, j, k) {
+        A[i * M + j] = smw ? tau * ws->Minv[i * M + j] + ws->G[i * M + j] : ws->Minv[i * M + j];
+    } KS_END2
+    KS_SYNC();
+    if (!lu_factor(A, k, ws->pw)) { KS_MASTER st->err[0] = DD4ML_ERR_SINGULAR; KS_SYNC(); return; }
+    lu_solve_cols(A, ws->pw, k, x, 1, 1);
+    KS_PAR(i, k) {
         const int pi = (int)st->order[i];
         st->cY[pi] = x[i];
         st->cS[pi] = -gam * x[i];
     }
+    KS_SYNC();
 }
+KS_FN inline void lsr1_B_coefs(dd4ml_state* st, Scratch* ws) { coefs_B_or_smw(st, ws, false); }
+KS_FN inline void smw_coefs(dd4ml_state* st, Scratch* ws) { coefs_B_or_smw(st, ws, true); }
 
-// rho and the accept decision of TR.step (tr.py:186-191), in the loss dtype T.
+// rho and the accept decision of TR.step (tr.py:186-191), in the loss dtype T.  Pure.
 template <class T>
 KS_FN inline bool tr_accept(double loss, double trial, double pred, double tol, double nu_dec, double* rho_out) {
     if (fabs((double)(T)pred) < tol) {
@@ -741,39 +844,46 @@ KS_FN inline bool tr_accept(double loss, double trial, double pred, double tol, 
 
 // Radius update + L-SR1 memory update after the trial evaluation (tr.py:191-221).
 // `accept` was decided by tr_accept; on acceptance the candidate reductions c_* and
-// out_gg / out_ginf (norms of the trial gradient) have been filled by the kernel.
+// out_gg / out_ginf (norms of the trial gradient) have been filled by the kernel.  Collective.
+KS_BIG inline void tr_finish(dd4ml_state* st, bool accept, double rho, bool f32, Scratch* ws) {
+    const double delta = st->delta[0], tol = st->tol[0];
+    const bool so = st->second_order[0] != 0.0;
+    const double pnorm = st->pnorm[0];
+    const bool try_pair = accept && so && dsqrt(st->c_ss[0]) > tol && dsqrt(st->c_yy[0]) > tol;  // tr.py:202
+    KS_SYNC();
+    KS_MASTER {
+        st->rho[0] = rho;
+        st->accept[0] = accept ? 1.0 : 0.0;
+        st->pair_tried[0] = try_pair ? 1.0 : 0.0;
+        st->pair_ok[0] = 0.0;
+        st->steps[0] += 1.0;
+    }
+    KS_SYNC();
+    if (try_pair) lsr1_try_update(st, ws);
+    KS_MASTER {
+        if (accept) {
+            if (rT(rho, f32) > rT(st->nu_inc[0], f32) && rT(pnorm, f32) >= rT(0.9 * delta, f32)) {  // tr.py:207
+                const double d = st->inc_factor[0] * delta;
+                st->delta[0] = (st->max_delta[0] < d) ? st->max_delta[0] : d;
+            }
+            st->out_gn[0] = rT((st->norm_inf[0] != 0.0) ? st->out_ginf[0] : dsqrt(st->out_gg[0]), f32);
+        } else {
+            const double d = st->dec_factor[0] * delta;
+            st->delta[0] = (st->min_delta[0] > d) ? st->min_delta[0] : d;
+            st->out_gn[0] = st->gn[0];
+            st->out_gg[0] = st->gg[0];
+            st->out_ginf[0] = st->ginf[0];
+        }
+    }
+    KS_SYNC();
+}
 template <class T>
 KS_FN inline void tr_finish(dd4ml_state* st, bool accept, double rho, Scratch* ws) {
-    st->rho[0] = rho;
-    st->accept[0] = accept ? 1.0 : 0.0;
-    st->pair_tried[0] = 0.0;
-    st->pair_ok[0] = 0.0;
-    st->steps[0] += 1.0;
-    const double delta = st->delta[0];
-    if (accept) {
-        if (st->second_order[0] != 0.0) {
-            const double tol = st->tol[0];
-            if (sqrt(st->c_ss[0]) > tol && sqrt(st->c_yy[0]) > tol) {  // tr.py:202
-                st->pair_tried[0] = 1.0;
-                lsr1_try_update(st, ws);
-            }
-        }
-        if ((T)rho > (T)st->nu_inc[0] && (T)st->pnorm[0] >= (T)(0.9 * delta)) {  // tr.py:207
-            const double d = st->inc_factor[0] * delta;
-            st->delta[0] = (st->max_delta[0] < d) ? st->max_delta[0] : d;
-        }
-        st->out_gn[0] = (double)(T)((st->norm_inf[0] != 0.0) ? st->out_ginf[0] : sqrt(st->out_gg[0]));
-    } else {
-        const double d = st->dec_factor[0] * delta;
-        st->delta[0] = (st->min_delta[0] > d) ? st->min_delta[0] : d;
-        st->out_gn[0] = st->gn[0];
-        st->out_gg[0] = st->gg[0];
-        st->out_ginf[0] = st->ginf[0];
-    }
+    tr_finish(st, accept, rho, sizeof(T) == 4, ws);
 }
 
 // APTS_Base.control_step decision (apts_base.py:483-501): reject when pred < tol or
-// rho < nu_dec; enlarge when rho > nu_inc.  delta is the APTS-level radius.
+// rho < nu_dec; enlarge when rho > nu_inc.  delta is the APTS-level radius.  Single thread.
 template <class T>
 KS_FN inline bool apts_accept(double f0, double ftrial, double pred, double tol, double nu_dec) {
     double rho;
@@ -808,5 +918,3 @@ KS_FN inline bool apts_control(dd4ml_state* st, double f0, double ftrial, double
 }
 
 }  // namespace ks
-
-#include "kspace_small.h"

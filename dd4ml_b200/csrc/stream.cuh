@@ -8,13 +8,16 @@
 //   * warp-shuffle -> shared-memory block reduction,
 //   * a deterministic two-stage finish: per-CTA partials + "last CTA done" ticket, the
 //     last CTA sums the partials (one warp per column, a fixed tree for a given grid) and
-//     then runs the k-space routine of the op (csrc/kspace.h) -- no host round trip.
+//     stores the sums in the device state block; the k-space work on them (L-SR1 update chain,
+//     OBS / dogleg solve ...) runs in the one-warp k-space kernel that is enqueued right behind
+//     with programmatic dependent launch (kspace_task.h) -- no host round trip.
 // The Ops below fuse what the reference does with 10-40 ATen launches per TR step.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/dd4ml_b200.h"
 #include "kspace.h"
+#include "kspace_task.h"
 
 namespace {
 
@@ -199,7 +202,6 @@ __device__ __forceinline__ void finish_reduce(Op& op, double* acc, double* ws) {
         __shared__ double s_red[NW][NRA];
         __shared__ double s_sum[NRA];
         __shared__ int s_last;
-        __shared__ ks::Scratch s_scratch;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
@@ -245,33 +247,16 @@ __device__ __forceinline__ void finish_reduce(Op& op, double* acc, double* ws) {
                 if (lane == 0) s_sum[j] = v;
             }
             __syncthreads();
-            if constexpr (Op::SMEM_STATE) {
-                // The k-space routine touches the state block hundreds of times: stage it in
-                // shared memory (3 KB) instead of paying an L2 round trip per access.
-                __shared__ dd4ml_state s_state;
-                constexpr int NST = (int)(sizeof(dd4ml_state) / sizeof(double));
-                double* gst = reinterpret_cast<double*>(op.state());
-                double* sst = reinterpret_cast<double*>(&s_state);
-                for (int i = threadIdx.x; i < NST; i += NW * 32) sst[i] = __ldcg(gst + i);
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    *ticket = 0u;
-                    op.finalize(s_sum, &s_scratch, &s_state);
-                    if (s_state.err[0] != 0.0) s_state.err_seen[0] = s_state.err[0];
-                }
-                __syncthreads();
-                for (int i = threadIdx.x; i < NST; i += NW * 32) gst[i] = sst[i];
-            } else {
-                if (threadIdx.x == 0) {
-                    *ticket = 0u;
-                    op.finalize(s_sum, &s_scratch, op.state());
-                    dd4ml_state* gs = op.state();
-                    if (gs != nullptr && gs->err[0] != 0.0) gs->err_seen[0] = gs->err[0];
-                }
+            if (threadIdx.x == 0) {
+                *ticket = 0u;
+                op.finalize(s_sum, op.state());
             }
         }
     }
 }
+
+// programmatic dependent launch: let the k-space kernel that follows become resident now
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 
 // ------------------------------------------------------------------ the streaming kernel
 template <class Op>
@@ -281,6 +266,7 @@ __global__ void __launch_bounds__(BLOCK) stream_kernel(Op op, int64_t n, int vec
     double acc[NRA];
 #pragma unroll
     for (int j = 0; j < NRA; ++j) acc[j] = 0.0;
+    pdl_trigger();
     op.setup();
     if (op.active()) {
         const int64_t tid = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -334,3 +320,16 @@ inline int launch(Op op, int64_t n, bool vec, double* ws, int per_sm, cudaStream
     else if (ht == 1 && vt == 1) { CALL(double, double) }                         \
     else return DD4ML_E_DTYPE;
 
+
+// variants that assign a return code instead of returning (the entry point goes on to enqueue
+// the k-space kernel)
+#define DT_SWITCH3_RC(ht, vt, wt, CALL)                                           \
+    if (ht == 0 && vt == 0 && wt == 0) { CALL(float, float, float) }              \
+    else if (ht == 0 && vt == 0 && wt == 1) { CALL(float, float, double) }        \
+    else if (ht == 0 && vt == 1 && wt == 1) { CALL(float, double, double) }       \
+    else if (ht == 1 && vt == 1 && wt == 1) { CALL(double, double, double) }
+
+#define DT_SWITCH2_RC(ht, vt, CALL)                                               \
+    if (ht == 0 && vt == 0) { CALL(float, float) }                                \
+    else if (ht == 0 && vt == 1) { CALL(float, double) }                          \
+    else if (ht == 1 && vt == 1) { CALL(double, double) }

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__((CW + PW) * 32, 1) tma_kernel(Op op, int64_t n
     constexpr int NR = Op::NRED;
     constexpr int NRA = NR > 0 ? NR : 1;
     constexpr int STAGE_BYTES = Op::NS_MAX * STREAM_BYTES;
+    pdl_trigger();
     op.setup();
     const bool producer = threadIdx.x >= CT;
     const int64_t nv4 = n & ~(int64_t)3;

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY: compiles dd4ml_b200/csrc/kspace.h for the host so that the
-// k-space routines (the exact source the CUDA kernels run in their last CTA) can be
-// checked against the oracle without a GPU.  Never loaded by the product package.
+// k-space routines (the exact source the one-warp k-space kernel runs; its parallel regions
+// become plain loops here, see the execution model in kspace.h) can be checked against the
+// oracle without a GPU.  Never loaded by the product package.
 #include "../../dd4ml_b200/csrc/kspace.h"
 #include "../../dd4ml_b200/csrc/state_table.h"
 
@@ -49,8 +50,9 @@ void hostshim_secular(int mode, double x0, const double* Lam, const double* a, i
 }
 int hostshim_eigh(const double* A, int k, double* w, double* V) {
     double a[ks::M * ks::M], v[ks::M * ks::M], ww[ks::M];
+    ks::Scratch ws;
     for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) a[i * ks::M + j] = A[i * k + j];
-    ks::jacobi_eigh(a, k, ww, v);
+    ks::jacobi_eigh(a, k, ww, v, &ws);
     for (int i = 0; i < k; ++i) { w[i] = ww[i]; for (int j = 0; j < k; ++j) V[i * k + j] = v[i * ks::M + j]; }
     return 0;
 }
