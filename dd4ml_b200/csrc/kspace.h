@@ -422,8 +422,10 @@ KS_BIG inline void build_compact(const dd4ml_state* st, Scratch* ws) {
         const double ss = st->SS[pi * MS + pj], yy = st->YY[pi * MS + pj];
         ws->Minv[i * M + j] = ((i >= j) ? sy_ij : sy_ji) - gam * ss;
         ws->G[i * M + j] = yy - gam * (sy_ij + sy_ji) + gam * gam * ss;
+        if (st->use_mx[0] != 0.0) ws->Minv[i * M + j] = st->Mx[i * M + j];   // explicit Minv (already regularised)
     } KS_END2
     KS_SYNC();
+    if (st->use_mx[0] != 0.0) return;
     KS_PAR(i, k) ws->Dw[i] = dots(ws->Minv + i * M, 1, ws->Minv + i * M, 1, k);   // row sums of squares
     KS_SYNC();
     double fro = 0.0;

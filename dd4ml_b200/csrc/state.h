@@ -41,7 +41,11 @@
     X(cg, 1) X(cS, DD4ML_MAXS) X(cY, DD4ML_MAXS)                                      \
     /* ---- candidate pair reductions (decide / begin kernels) ---- */                \
     X(c_ss, 1) X(c_sy, 1) X(c_yy, 1) X(c_sg, 1) X(c_yg, 1)                            \
-    X(c_Ss, DD4ML_MAXS) X(c_Ys, DD4ML_MAXS) X(c_Sy, DD4ML_MAXS) X(c_Yy, DD4ML_MAXS)
+    X(c_Ss, DD4ML_MAXS) X(c_Ys, DD4ML_MAXS) X(c_Sy, DD4ML_MAXS) X(c_Yy, DD4ML_MAXS)                  \
+    /* ---- caller-supplied M^{-1} (OBS.solve_tr_subproblem / ComputeSBySMW with explicit Psi, Minv:  */ \
+    /* obs.py:46,175): logical order, leading dimension DD4ML_MAXM; used instead of the Gram-derived  */ \
+    /* matrix while use_mx != 0                                                                       */ \
+    X(use_mx, 1) X(Mx, DD4ML_MAXM * DD4ML_MAXM)
 
 struct dd4ml_state {
 #define X(name, count) double name[count];

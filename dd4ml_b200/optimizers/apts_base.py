@@ -24,10 +24,11 @@ from .. import _lib
 from .._device import DeviceState
 from ..flat import get_flat
 from ..graphs import GraphedEval
-from ..utility.optimizer_utils import (get_apts_hparams, get_loc_tr_hparams, get_lssr1_loc_tr_hparams,
-                                       get_lssr1_tr_hparams, get_tr_hparams)
+from ..utility.optimizer_utils import (get_apts_hparams, get_loc_tr_hparams, get_loc_tradam_hparams,
+                                       get_lssr1_loc_tr_hparams, get_lssr1_tr_hparams, get_tr_hparams)
 from .lssr1_tr import LSSR1_TR
 from .tr import TR, as_device_scalar
+from .tradam import TRAdam
 
 
 COMM_PROF = None      # bench.py: list of (start_event, end_event, numel) per collective when profiling
@@ -50,9 +51,14 @@ class APTS_Base(Optimizer):
 
     @staticmethod
     def setup_APTS_hparams(config):
-        """apts_base.py:40-83: resolve 'tr' / 'lssr1_tr' to the B200 classes + hparam tables."""
+        """apts_base.py:40-83: resolve the optimizer names to the B200 classes + hparam tables.  `tradam` and
+        `sgd` are accepted as local optimizers exactly as the reference accepts them (apts_base.py:50-55): under
+        APTS the reference drives TRAdam with closures that do not back-propagate (:379-382) so its local phase
+        leaves the parameters unchanged, and a `torch.optim.SGD` local optimizer raises TypeError on the first
+        local step (:384-390) -- both behaviours are kept (tests/test_gpu_optimizers.py)."""
         glob_map = {"tr": (TR, get_tr_hparams), "lssr1_tr": (LSSR1_TR, get_lssr1_tr_hparams)}
-        loc_map = {"tr": (TR, get_loc_tr_hparams), "lssr1_tr": (LSSR1_TR, get_lssr1_loc_tr_hparams)}
+        loc_map = {"tr": (TR, get_loc_tr_hparams), "lssr1_tr": (LSSR1_TR, get_lssr1_loc_tr_hparams),
+                   "tradam": (TRAdam, get_loc_tradam_hparams), "sgd": (torch.optim.SGD, lambda _: {"lr": 0.01})}
         if not isinstance(config.glob_opt, str):
             raise ValueError("glob_opt must be a string specifying the optimizer type, e.g., 'tr' or 'lssr1_tr'.")
         try:
@@ -66,7 +72,7 @@ class APTS_Base(Optimizer):
         try:
             config.loc_opt, fn = loc_map[loc_value.lower()]
         except KeyError:
-            raise ValueError(f"Unknown loc_opt: {loc_value} (dd4ml_b200 provides 'tr' and 'lssr1_tr')")
+            raise ValueError(f"Unknown loc_opt: {loc_value}")
         config.loc_opt_hparams = fn(config)
         config.apts_params = get_apts_hparams(config)
         return config
@@ -311,16 +317,23 @@ class APTS_Base(Optimizer):
         if closure is None:
             raise ValueError("Closure must be provided for global/local optimization step in APTS.")
         for _ in range(max_iters):
-            loss, grad = optim.step(closure=closure, loss=loss, grad=grad)
+            if isinstance(optim, (TR, LSSR1_TR)):
+                loss, grad = optim.step(closure=closure, loss=loss, grad=grad)
+            elif isinstance(optim, TRAdam):                  # apts_base.py:379-382
+                loss = optim.step(closure=closure)
+                grad = optim._flat_grad()
+            else:                                            # apts_base.py:384-390 (ASNTR call form)
+                loss, grad = optim.step(closure_main=closure, closure_d=closure_d, loss=loss, grad=grad)
             if getattr(optim, "device_control", False):
                 continue        # converged steps are predicated no-ops on the device
-            if hasattr(optim, "tol") and self._grad_norm_of(optim, grad) <= optim.tol:
+            if hasattr(optim, "tol") and self._grad_norm_of(optim, grad) <= optim.tol:   # apts_base.py:397
                 break
         return loss, grad
 
     def loc_steps(self, loss, grad):
         """apts_base.py:402-418; the rank-averaged evaluation counter rides in the step all-reduce."""
-        return self._step_loop(self.loc_opt, self.max_loc_iters, loss, grad, closure=self.loc_closure)
+        return self._step_loop(self.loc_opt, self.max_loc_iters, loss, grad, closure=self.loc_closure,
+                               closure_d=self.loc_closure_d)
 
     def glob_steps(self, loss, grad, closure=None, closure_d=None):
         return self._step_loop(self.glob_opt, self.max_glob_iters, loss, grad,

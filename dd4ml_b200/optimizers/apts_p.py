@@ -53,7 +53,15 @@ class APTS_P(APTS_Base):
         self._lfb = fb
         self._lfs = FlatSlice(fb, 0, fb.n)
         owned = [lps[i] for i in owned_idx]
-        self.loc_opt = loc_opt(params=owned, **loc_opt_hparams)
+        from .lssr1_tr import LSSR1_TR
+        from .tr import TR
+        if issubclass(loc_opt, (TR, LSSR1_TR)):
+            self.loc_opt = loc_opt(params=owned, **loc_opt_hparams)
+        else:
+            # apts_p.py:76-81 hands every local optimizer the flat hooks: TRAdam takes them, a stock
+            # torch optimizer (loc_opt: sgd) raises TypeError here, as in the reference
+            self.loc_opt = loc_opt(params=owned, flat_grads_fn=self.loc_grad_to_vector,
+                                   flat_params_fn=self.loc_params_to_vector, **loc_opt_hparams)
         # the reference passes flat_grads_fn / flat_params_fn hooks to this optimizer (apts_p.py:76-81):
         # its vectors bypass the construction-dtype flat buffers of TR / LSSR1_TR
         self.loc_opt._ref_hooks = True

@@ -1,11 +1,14 @@
 """OBS (orthonormal-basis SR1) trust-region sub-problem solver, drop-in name for
 ``dd4ml.solvers.obs.OBS`` (obs.py:26-254).
 
-On the hot path the OBS computation is not a separate call: it runs in k-space inside the
-last CTA of ``tr_propose`` / ``lssr1_begin`` (csrc/kspace.h ``tr_solve``), fed by the Gram
-blocks of the L-SR1 pairs.  This class keeps the reference's entry point for callers that
-hold an ``LSR1`` object: ``solve_tr_subproblem(g, delta, gamma, Psi, Minv)`` accepts the
-owning ``LSR1`` in place of ``Psi`` (its Psi / Minv are implicit) and returns p*.
+On the hot path the OBS computation is not a separate call: it runs in the one-warp k-space
+kernel behind ``tr_propose`` / ``lssr1_begin`` (csrc/kspace.h ``tr_solve``), fed by the Gram
+blocks of the L-SR1 pairs.  This class keeps the reference's entry points:
+``solve_tr_subproblem(g, delta, gamma, Psi, Minv)`` and ``ComputeSBySMW(tau, g, PsiTg, Psi, Minv,
+PsiPsi)`` accept either the owning ``LSR1`` in place of ``Psi`` (its Psi / Minv are implicit) or the
+explicit (n x k) ``Psi`` and (k x k) ``Minv`` tensors of the reference signature (obs.py:46,175):
+the explicit form runs the same kernels on a scratch L-SR1 block with S = 0, Y = Psi^T, so that
+Y - gamma S = Psi, and the caller's Minv in the state block (``use_mx``).
 """
 from __future__ import annotations
 
@@ -19,19 +22,54 @@ class OBS:
         self.tol = 1e-6          # obs.py:29
         self.last: dict = {}     # diagnostics of the last solve (case, sigma*, Newton iterations)
 
+    @staticmethod
+    def _explicit(Psi: torch.Tensor, Minv: torch.Tensor, gamma):
+        """Scratch L-SR1 block that represents the caller's explicit (Psi, Minv, gamma)."""
+        from ..optimizers.lsr1 import LSR1
+        if not (torch.is_tensor(Psi) and Psi.dim() == 2 and torch.is_tensor(Minv) and Minv.dim() == 2):
+            raise TypeError("dd4ml_b200.OBS: `Psi` must be an LSR1 object or an (n x k) tensor with a (k x k) `Minv`")
+        n, k = Psi.shape
+        if Minv.shape != (k, k):
+            raise ValueError(f"Minv must be ({k} x {k}) for an (n x {k}) Psi")
+        if not Psi.is_cuda:
+            raise _lib.DD4MLError("dd4ml_b200 has no CPU path: Psi must live on a CUDA device")
+        dtype = Psi.dtype if Psi.dtype in (torch.float32, torch.float64) else torch.float32
+        h = LSR1(gamma=float(gamma), memory_length=max(k, 1), tol=1e-6, device=Psi.device, dtype=dtype)
+        if k > h.ds.lay.maxm:
+            raise _lib.DD4MLError(f"dd4ml_b200.OBS: k = {k} exceeds the build's maximum {h.ds.lay.maxm}")
+        h.ensure_storage(n)
+        lay, ms, mm = h.ds.lay, h.ds.lay.maxs, h.ds.lay.maxm
+        h._Ybuf[:k, :n].copy_(Psi.t())                        # S stays 0:  Y - gamma S = Psi
+        P64 = Psi.to(torch.float64)
+        yy = torch.zeros(ms, ms, dtype=torch.float64, device=Psi.device)
+        yy[:k, :k] = P64.t() @ P64                             # the k x k Gram block the kernels keep incrementally
+        mx = torch.zeros(mm, mm, dtype=torch.float64, device=Psi.device)
+        mx[:k, :k] = Minv.to(torch.float64)
+        st = h.ds.state
+        st[lay.slice("YY")].copy_(yy.reshape(-1))
+        st[lay.slice("Mx")].copy_(mx.reshape(-1))
+        st[lay.slice("order")].copy_(torch.arange(mm, dtype=torch.float64, device=Psi.device))
+        h.ds.set(k=k, spare=k, gamma=float(gamma), use_mx=1.0, second_order=1.0)
+        h._k_host, h._gamma_host = k, float(gamma)
+        return h
+
     def solve_tr_subproblem(self, g, delta, gamma, Psi, Minv=None):
         from ..optimizers.lsr1 import LSR1
         from ..utility.optimizer_utils import solve_tr_second_order
-        if not isinstance(Psi, LSR1):
-            raise TypeError(
-                "dd4ml_b200.OBS works on the device-resident L-SR1 state: pass the LSR1 object as `Psi` "
-                "(explicit (n x k) Psi / Minv matrices are never materialised in this implementation)")
-        h = Psi
         for name, t in (("g", g), ("delta", torch.as_tensor(delta)), ("gamma", torch.as_tensor(gamma))):
             if torch.isnan(t).any() or torch.isinf(t).any():
                 raise ValueError(f"{name} contains NaN or Inf values")
         if float(delta) < 0:
             raise ValueError("Delta must be non-negative")
+        if not isinstance(Psi, LSR1):
+            for name, t in (("Psi", Psi), ("Minv", Minv)):                    # obs.py:54-57
+                if torch.is_tensor(t) and (torch.isnan(t).any() or torch.isinf(t).any()):
+                    raise ValueError(f"{name} contains NaN or Inf values")
+            h = self._explicit(Psi, Minv, gamma)
+            # (the reference's OBS has no ||g|| <= tol exit: solve whatever the gradient norm)
+            p, _ = solve_tr_second_order(g, torch.norm(g), float(delta), h, self, 0.0, dogleg=False)
+            return p
+        h = Psi
         dog = h.ds.read().dogleg
         p, _ = solve_tr_second_order(g, torch.norm(g), float(delta), h, self, h.tol, dogleg=False)
         h.ds.set(dogleg=dog)
@@ -73,7 +111,7 @@ class OBS:
         from .._device import DeviceState
         from ..optimizers.lsr1 import LSR1
         if not isinstance(Psi, LSR1):
-            raise TypeError("dd4ml_b200.OBS.ComputeSBySMW: pass the LSR1 object as `Psi`")
+            Psi = self._explicit(Psi, Minv, 1.0)      # gamma does not enter the SMW formula (obs.py:175-182)
         h, ds = Psi, Psi.ds
         g = g.detach().contiguous()
         n, vt = g.numel(), _lib.dt(g.dtype)

@@ -559,6 +559,10 @@ def main():
         torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
         run_config5_all()
         return
+    if "--only-tradam-loc" in sys.argv:
+        torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+        run_apts("apts_d_tr_tradam_ws1", "apts_d", 1, "tr", "tradam", False, False, 3, 6, port=29661)
+        return
     if "--only-ws8" in sys.argv:
         torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
         run_apts("apts_d_tr_fo_ws8", "apts_d", 8, "tr", "tr", False, False, 3, 8, port=29651)
@@ -600,6 +604,7 @@ def main():
     run_pinn("apts_pinn_ws2", 2, 10, port=29609)
     run_apts("apts_d_tr_fo_ws8", "apts_d", 8, "tr", "tr", False, False, 3, 8, port=29651)
     run_apts("apts_d_lssr1_fo_ws8", "apts_d", 8, "lssr1_tr", "lssr1_tr", False, False, 3, 8, port=29652)
+    run_apts("apts_d_tr_tradam_ws1", "apts_d", 1, "tr", "tradam", False, False, 3, 6, port=29661)
     run_config5_all()
     run_tradam("tradam_inf", math.inf, 0.01, 20)
     run_tradam("tradam_l2", 2, 0.5, 20)

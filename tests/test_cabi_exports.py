@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -102,3 +104,61 @@ def test_install_overlays_reference_module_paths(monkeypatch):
     finally:
         for k in done:
             sys.modules.pop(k, None)
+
+
+def _reference_src():
+    for root in ("/root/reference/src", os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(root, "dd4ml")):
+            return root
+    return None
+
+
+@pytest.mark.skipif(_reference_src() is None, reason="reference package not available on this box")
+def test_hparam_tables_equal_the_reference_functions():
+    """Every hyper-parameter getter (optimizer_utils.py:27-164) and `setup_APTS_hparams` (apts_base.py:40-83)
+    diffed against the reference's own functions over a grid of configs, in a subprocess (the reference's
+    modules and the install() overlay must not leak into this interpreter)."""
+    import subprocess
+    import sys
+    code = r'''
+import itertools, math, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import dd4ml.utility as RU
+from dd4ml.utility import CfgNode
+from dd4ml.optimizers.apts_base import APTS_Base as RefBase
+import dd4ml_b200.utility.optimizer_utils as OU
+from dd4ml_b200.optimizers.apts_base import APTS_Base as OurBase
+import torch.distributed as dist
+names = ["get_apts_hparams", "get_lssr1_tr_hparams", "get_lssr1_loc_tr_hparams", "get_tr_hparams",
+         "get_loc_tr_hparams", "get_loc_tradam_hparams"]
+n = 0
+for ws in (1, 2):
+    if ws == 2:
+        import os
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", "29921"
+        # the local tables scale radii by 1 / world_size (optimizer_utils.py:11-15): fake a 2-rank world
+        import unittest.mock as um
+        p1 = um.patch("torch.distributed.is_initialized", return_value=True); p1.start()
+        p2 = um.patch("torch.distributed.get_world_size", return_value=2); p2.start()
+    for norm, so, dog, m, paper in itertools.product((2, math.inf), (False, True), (False, True), (3, 5, 10), (False, True)):
+        if dog and not so:
+            continue
+        kw = dict(delta=0.07, min_delta=0.003, max_delta=1.7, norm_type=norm, glob_second_order=so, glob_dogleg=dog,
+                  loc_second_order=so, loc_dogleg=dog, mem_length=m, max_wolfe_iters=4, max_zoom_iters=6, tol=1e-7,
+                  paper_tr_update=paper, learning_rate=0.02, glob_opt="lssr1_tr", loc_opt="tr")
+        for name in names:
+            a, b = getattr(RU, name)(CfgNode(**kw)), getattr(OU, name)(CfgNode(**kw))
+            assert a == b, (name, kw, a, b)
+            n += 1
+        for glob, loc in (("tr", "tr"), ("lssr1_tr", "lssr1_tr"), ("tr", "tradam"), ("lssr1_tr", "sgd")):
+            ra = RefBase.setup_APTS_hparams(CfgNode(**dict(kw, glob_opt=glob, loc_opt=loc)))
+            oa = OurBase.setup_APTS_hparams(CfgNode(**dict(kw, glob_opt=glob, loc_opt=loc)))
+            assert ra.glob_opt.__name__ == oa.glob_opt.__name__ and ra.loc_opt.__name__ == oa.loc_opt.__name__
+            assert ra.glob_opt_hparams == oa.glob_opt_hparams and ra.loc_opt_hparams == oa.loc_opt_hparams
+            assert ra.apts_params == oa.apts_params
+            n += 1
+print("compared", n)
+''' % (_reference_src(), ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "compared" in r.stdout and int(r.stdout.split()[-1]) > 300

@@ -386,3 +386,43 @@ def test_obs_stand_alone_helpers_match_oracle():
         p_ref = -g.double() / tau + Psi @ torch.linalg.solve(W, Psi.t() @ g.double())
         p = obs.ComputeSBySMW(tau, g.to(DEV), None, h, None, None)
         assert rel_err(p.cpu(), p_ref) < 1e-5
+
+
+def test_obs_explicit_psi_minv_signature_matches_oracle():
+    """The reference signature with explicit matrices: OBS.solve_tr_subproblem(g, delta, gamma, Psi, Minv)
+    (obs.py:46-173) and OBS.ComputeSBySMW(tau, g, PsiTg, Psi, Minv, PsiPsi) (obs.py:175-182) with (n x k) Psi and
+    (k x k) Minv tensors, against the oracle on the same matrices and against the LSR1-object form."""
+    from oracle.obs import obs_solve
+    torch.manual_seed(5)
+    n = 20000
+    obs = dd4ml_b200.OBS()
+    d = torch.linspace(-0.5, 3.0, n)                       # indefinite: cases A and C both occur
+    for m, dtype, tol in ((3, torch.float32, 1e-5), (5, torch.float64, 1e-9)):
+        hc = LSR1Memory(gamma=1.0, memory_length=m, tol=1e-6, dtype=dtype)
+        h = LSR1(gamma=1.0, memory_length=m, tol=1e-6, device=DEV, dtype=dtype)
+        for _ in range(m):
+            s = (torch.randn(n) * 0.05).to(dtype)
+            y = (d * s + 1e-3 * torch.randn(n)).to(dtype)
+            if hc.update(s, y):
+                h.update_memory(s.to(DEV), y.to(DEV))
+        hc.precompute()
+        Psi, Minv, gamma = hc.Psi, hc.Minv, hc.gamma
+        g = torch.randn(n).to(dtype)
+        for delta in (0.05, 1.0, 50.0):
+            info = {}
+            p_ref = obs_solve(g, torch.tensor(delta, dtype=dtype), gamma, Psi, Minv, eig_sign="canonical", info=info)
+            p = obs.solve_tr_subproblem(g.to(DEV), delta, float(gamma), Psi.to(DEV), Minv.to(DEV))
+            assert p.dtype == dtype and rel_err(p.cpu(), p_ref) < tol, (m, delta, info.get("case"))
+            assert {1: "A", 3: "C"}[obs.last["case"]] == info["case"]
+            p_obj = obs.solve_tr_subproblem(g.to(DEV), delta, float(gamma), h)
+            assert rel_err(p.cpu(), p_obj.cpu()) < tol
+        tau = 2.5
+        W = tau * Minv.double() + Psi.double().t() @ Psi.double()
+        s_ref = -g.double() / tau + Psi.double() @ torch.linalg.solve(W, Psi.double().t() @ g.double())
+        sp = obs.ComputeSBySMW(tau, g.to(DEV), None, Psi.to(DEV), Minv.to(DEV), None)
+        assert rel_err(sp.cpu(), s_ref) < tol
+    with pytest.raises(ValueError, match="NaN or Inf"):
+        bad = Psi.clone(); bad[0, 0] = float("nan")
+        obs.solve_tr_subproblem(g.to(DEV), 1.0, 1.0, bad.to(DEV), Minv.to(DEV))
+    with pytest.raises(ValueError, match="non-negative"):
+        obs.solve_tr_subproblem(g.to(DEV), -1.0, 1.0, Psi.to(DEV), Minv.to(DEV))

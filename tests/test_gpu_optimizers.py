@@ -250,6 +250,42 @@ def test_apts_d_single_rank_matches_reference(device_control, monkeypatch):
     assert torch.equal(flat_of(opt.loc_model), flat_of(model))
 
 
+def test_apts_d_loc_opt_tradam_matches_reference():
+    """`loc_opt: tradam` (apts_base.py:50-55): the reference steps TRAdam with closures that do not
+    back-propagate (:379-382), so the local phase leaves the clone unchanged, the combined step is zero,
+    `pred < tol` rejects it (:490) and only the global pass moves -- reproduced against a golden of the
+    unmodified reference (radius 0.1 -> 0.108 -> ...)."""
+    g = load_golden("apts_d_tr_tradam_ws1")
+    X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
+    model = gpu_model(g)
+    opt = _apts("d", model, "tr", "tradam", cfg(learning_rate=0.1), foc=True)
+    assert type(opt.loc_opt).__name__ == "TRAdam" and not opt._device_control
+    losses, deltas, gev = [], [], []
+    for _ in range(int(g["steps"])):
+        losses.append(float(opt.step(X, Y)))
+        deltas.append(float(opt.delta)); gev.append(opt.grad_evals)
+    np.testing.assert_allclose(losses, g["loss"], rtol=2e-4)
+    np.testing.assert_allclose(deltas, g["delta"], rtol=1e-9)
+    np.testing.assert_allclose(gev, g["grad_evals"], atol=1e-9)
+    assert rel_err(flat_of(model), g["w_final"]) < 1e-3
+
+
+def test_apts_loc_opt_sgd_raises_like_the_reference():
+    """`loc_opt: sgd` is accepted by setup_APTS_hparams (apts_base.py:54) and constructed, and the first local
+    step fails with TypeError (`SGD.step() got an unexpected keyword argument 'closure_main'`, :384-390);
+    APTS_P hands the flat hooks to the constructor (apts_p.py:76-81) and fails there.  Same error type."""
+    g = load_golden("apts_d_tr_fo_ws1")
+    X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
+    opt = _apts("d", gpu_model(g), "tr", "sgd", cfg(), foc=True)
+    assert isinstance(opt.loc_opt, torch.optim.SGD)
+    with pytest.raises(TypeError, match="closure_main"):
+        opt.step(X, Y)
+    with pytest.raises(TypeError):
+        _apts("p", gpu_model(g), "tr", "sgd", cfg(norm_type=math.inf, max_delta=0.5))
+    with pytest.raises(ValueError, match="Unknown loc_opt"):
+        _apts("d", gpu_model(g), "tr", "adamw", cfg())
+
+
 @pytest.mark.parametrize("glob,loc,so,dog", [("lssr1_tr", "lssr1_tr", True, True), ("tr", "tr", True, False),
                                              ("lssr1_tr", "tr", False, False)])
 def test_apts_d_single_rank_matches_oracle(glob, loc, so, dog):
