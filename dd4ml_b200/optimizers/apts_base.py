@@ -169,6 +169,38 @@ class APTS_Base(Optimizer):
         # (its radius is re-derived from the global one at the end of every outer iteration)
         if type(self.loc_opt) is TR:
             self.loc_opt.device_control = env_on and loc_tr
+        self._configure_speculation()
+
+    @staticmethod
+    def closure_has_side_effects(model) -> bool:
+        """True when an extra forward pass would be observable: dropout consumes RNG state, BatchNorm
+        updates running statistics.  Models that draw random numbers without using
+        nn.Dropout modules can declare it with an attribute `stochastic_forward = True`."""
+        base = model.module if hasattr(model, "module") else model
+        if getattr(base, "stochastic_forward", False):
+            return True
+        for m in base.modules():
+            if isinstance(m, torch.nn.modules.dropout._DropoutNd) and m.p > 0:
+                return True
+            if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.track_running_stats:
+                return True
+            if isinstance(m, (torch.nn.RNNBase, torch.nn.MultiheadAttention)) and getattr(m, "dropout", 0) > 0:
+                return True
+        return False
+
+    def _configure_speculation(self):
+        """LSSR1_TR inner optimizers may launch the first line-search evaluation before the convergence
+        test has been read (one host read less per step).  The only difference from the reference's
+        closure-call sequence is one extra evaluation when ||g|| <= tol, so it is enabled only for
+        models whose forward pass has no side effects, and never when DD4ML_B200_SPECULATIVE=0 or
+        DD4ML_B200_DEVICE_CONTROL=0."""
+        on = (os.environ.get("DD4ML_B200_DEVICE_CONTROL", "1") != "0"
+              and os.environ.get("DD4ML_B200_SPECULATIVE", "1") != "0"
+              and not self.closure_has_side_effects(self.model))
+        for o in (self.glob_opt, self.loc_opt):
+            if isinstance(o, LSSR1_TR):
+                o.speculative_first_eval = on
+        return on
 
     def _link(self, dst, src, scale=1.0, lo=-math.inf, hi=math.inf):
         """dst.delta <- clamp(src.delta * scale, lo, hi) on the device."""

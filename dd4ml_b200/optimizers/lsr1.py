@@ -139,6 +139,32 @@ class LSR1:
         DeviceState.raise_for(rep.err)
         self.absorb(rep)
 
+    @torch.no_grad()
+    def set_memory(self, S: torch.Tensor, Y: torch.Tensor, gamma: float) -> None:
+        """Install k pairs (columns of the (n x k) matrices S, Y, oldest first) and gamma directly, bypassing
+        the acceptance chain -- what writing the reference's `_S_matrix` / `_Y_matrix` / `gamma` attributes
+        does (lsr1.py:112-120).  Compatibility / test utility (library GEMMs for the Gram blocks), not on
+        the hot path."""
+        S, Y = S.detach().to(self.device), Y.detach().to(self.device)
+        n, k = S.shape
+        if k > self.memory_length:
+            raise ValueError(f"{k} pairs exceed memory_length={self.memory_length}")
+        self._Sbuf = None
+        self._k_host = 0
+        self.ensure_storage(n)
+        lay, ms = self.ds.lay, self.ds.lay.maxs
+        self._Sbuf[:k, :n].copy_(S.t())
+        self._Ybuf[:k, :n].copy_(Y.t())
+        S64, Y64 = self._Sbuf[:k, :n].double(), self._Ybuf[:k, :n].double()      # (values as stored)
+        st = self.ds.state
+        for name, A, B in (("SS", S64, S64), ("SY", S64, Y64), ("YY", Y64, Y64)):
+            blk = torch.zeros(ms, ms, dtype=torch.float64, device=self.device)
+            blk[:k, :k] = A @ B.t()
+            st[lay.slice(name)].copy_(blk.reshape(-1))
+        st[lay.slice("order")].copy_(torch.arange(lay.maxm, dtype=torch.float64, device=self.device))
+        self.ds.set(k=k, spare=k, gamma=float(gamma), use_mx=0.0)
+        self._k_host, self._gamma_host = k, float(gamma)
+
     def precompute(self) -> None:
         """lsr1.py:146-179.  Nothing to do: Psi / M^{-1} are k-space quantities rebuilt from
         the Gram blocks inside the kernels.  Kept for API compatibility."""

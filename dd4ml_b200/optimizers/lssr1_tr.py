@@ -96,10 +96,13 @@ class LSSR1_TR(Optimizer):
             raise _lib.DD4MLError(
                 "dd4ml_b200 LSSR1_TR: flat_grads_fn/flat_params_fn hooks are not needed -- pass the "
                 "trainable parameters themselves (APTS_P lays them out contiguously)")
-        # Fold the convergence read into the read of the first line-search evaluation (always at
-        # alpha = alpha_max / 2): one host read less per step.  Only difference from the reference:
-        # when ||g|| <= tol the closure is evaluated once before the step returns.
-        self.speculative_first_eval = os.environ.get("DD4ML_B200_DEVICE_CONTROL", "1") != "0"
+        # Folding the convergence read into the read of the first line-search evaluation (always at
+        # alpha = alpha_max / 2) saves one host read per step, at the price of ONE closure call the
+        # reference does not make when ||g|| <= tol (it returns before the line search, lssr1_tr.py:509).
+        # Opt-in (DD4ML_B200_SPECULATIVE=1) for a stand-alone LSSR1_TR; the APTS classes switch it on for
+        # their inner optimizers only when the model's forward pass has no side effects (no dropout RNG,
+        # no BatchNorm running statistics): see APTS_Base._configure_speculation.
+        self.speculative_first_eval = os.environ.get("DD4ML_B200_SPECULATIVE", "0") == "1"
         self._pre = None
         self._bufs = None
         self._has_prev = False

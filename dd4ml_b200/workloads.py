@@ -194,7 +194,8 @@ class _GPTBlock(nn.Module):
         self.ln_1, self.ln_2 = nn.LayerNorm(d), nn.LayerNorm(d)
         self.c_attn, self.c_proj = nn.Linear(d, 3 * d), nn.Linear(d, d)
         self.c_fc, self.c_proj2 = nn.Linear(d, 4 * d), nn.Linear(4 * d, d)
-        self.heads, self.p = heads, p
+        self.heads = heads
+        self.attn_drop, self.resid_drop, self.mlp_drop = nn.Dropout(p), nn.Dropout(p), nn.Dropout(p)
         self.register_buffer("mask", torch.tril(torch.ones(block, block)).view(1, 1, block, block))
 
     def forward(self, x):
@@ -204,12 +205,12 @@ class _GPTBlock(nn.Module):
         q, k, v = sh(q), sh(k), sh(v)
         att = (q @ k.transpose(-2, -1)) * (1.0 / (k.size(-1) ** 0.5))
         att = att.masked_fill(self.mask[:, :, :T, :T] == 0, float("-inf"))
-        att = F.dropout(F.softmax(att, dim=-1), self.p, self.training)
+        att = self.attn_drop(F.softmax(att, dim=-1))
         y = (att @ v).transpose(1, 2).contiguous().view(B, T, C)
-        x = x + F.dropout(self.c_proj(y), self.p, self.training)
+        x = x + self.resid_drop(self.c_proj(y))
         h = self.c_fc(self.ln_2(x))
         h = 0.5 * h * (1.0 + torch.tanh(0.7978845608028654 * (h + 0.044715 * torch.pow(h, 3.0))))
-        return x + F.dropout(self.c_proj2(h), self.p, self.training)
+        return x + self.mlp_drop(self.c_proj2(h))
 
 
 class MiniGPT(nn.Module):
@@ -223,7 +224,7 @@ class MiniGPT(nn.Module):
         self.h = nn.ModuleList([_GPTBlock(d, heads, block, p_drop) for _ in range(layers)])
         self.ln_f = nn.LayerNorm(d)
         self.lm_head = nn.Linear(d, vocab, bias=False)
-        self.p = p_drop
+        self.drop = nn.Dropout(p_drop)
         for m in self.modules():                      # GPT-2 initialisation (model.py:83-92, 49-54)
             if isinstance(m, (nn.Linear, nn.Embedding)):
                 nn.init.normal_(m.weight, mean=0.0, std=0.02)
@@ -236,7 +237,7 @@ class MiniGPT(nn.Module):
     def forward(self, idx):
         T = idx.size(1)
         pos = torch.arange(T, device=idx.device).unsqueeze(0)
-        x = F.dropout(self.wte(idx) + self.wpe(pos), self.p, self.training)
+        x = self.drop(self.wte(idx) + self.wpe(pos))
         for blk in self.h:
             x = blk(x)
         return self.lm_head(self.ln_f(x))

@@ -96,3 +96,47 @@ def branch_distance(gpu_losses, oracle_run, k, seeds=10, eps=1e-6):
     gpu = np.asarray(gpu_losses[:k], dtype=np.float64)
     d = [float(np.max(np.abs(gpu - np.asarray(r[:k])) / np.abs(np.asarray(r[:k])))) for r in runs]
     return min(d), runs[int(np.argmin(d))]
+
+
+def sigma_spread(info, delta, gamma=None, dtype=torch.float32):
+    """How much the reference's OBS result depends on the (implementation-defined) signs LAPACK gives the
+    eigenvectors: relative spread of sigma* over all 2^k sign patterns of a_1..a_k (obs.py:162-170 starts
+    Newton from max_j(a_j/delta - Lambda_j) with SIGNED a_j; the last a is a norm).  0.0 = sign-insensitive.
+    `info` is the dict filled by oracle.obs_solve (Lambda, a, case)."""
+    import itertools
+    from oracle.obs import OBS_TOL, _newton
+    Lam, a = info["Lambda"].to(dtype), info["a"].to(dtype)
+    k = a.numel() - 1
+    lam_min = float(info["lam_min"]) if "lam_min" in info else min(float(Lam[0]), float(gamma))
+    if info["case"] != "C" or lam_min > 0:
+        return 0.0
+    d = torch.tensor(delta, dtype=dtype)
+    sig = []
+    for s in itertools.product((1.0, -1.0), repeat=k):
+        aa = a.clone()
+        aa[:k] = aa[:k] * torch.tensor(s, dtype=dtype)
+        sh = torch.max(aa / d - Lam)
+        x0 = sh if sh > -lam_min else torch.tensor(-lam_min, dtype=dtype)
+        sig.append(float(_newton(x0, Lam, aa, d, OBS_TOL)[0]))
+    return (max(sig) - min(sig)) / max(abs(max(sig)), 1e-30)
+
+
+def golden_solves(name):
+    """The sub-problem solves recorded inside a trajectory golden (gen_golden.SolveRecorder): dicts with
+    g, S, Y (n x k), gamma, delta, dogleg, p, pred of the UNMODIFIED reference."""
+    g = load_golden(name)
+    out = []
+    for i in range(int(g["n_solves"])):
+        out.append({k: g[f"solve{i}_{k}"] for k in ("g", "S", "Y", "gamma", "delta", "dogleg", "p", "pred", "tol")})
+    return out
+
+
+def oracle_memory(S, Y, gamma, dtype=torch.float32):
+    """LSR1Memory holding exactly the given pairs / gamma (bypasses the acceptance chain)."""
+    from oracle.lsr1 import LSR1Memory
+    S, Y = torch.as_tensor(S).to(dtype), torch.as_tensor(Y).to(dtype)
+    h = LSR1Memory(gamma=float(gamma), memory_length=max(S.shape[1], 1), tol=1e-6, dtype=dtype)
+    h.S = [S[:, j].clone() for j in range(S.shape[1])]
+    h.Y = [Y[:, j].clone() for j in range(Y.shape[1])]
+    h.gamma = torch.tensor(float(gamma), dtype=dtype)
+    return h

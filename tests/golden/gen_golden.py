@@ -133,10 +133,10 @@ def tr_kwargs(second_order, dogleg, norm_type=2):
     return get_tr_hparams(cfg)
 
 
-def run_plain(name, make_opt, steps, dtype=torch.float32):
+def run_plain(name, make_opt, steps, dtype=torch.float32, data_seed=1234):
     """Plain TR / LSSR1_TR as the top-level optimizer with an own closure."""
     model = make_model(dtype)
-    X, Y = make_data(256, dtype=dtype)
+    X, Y = make_data(256, seed=data_seed, dtype=dtype)
     crit = nn.CrossEntropyLoss()
     opt = make_opt(model)
 
@@ -563,6 +563,14 @@ def main():
         torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
         run_apts("apts_d_tr_tradam_ws1", "apts_d", 1, "tr", "tradam", False, False, 3, 6, port=29661)
         return
+    if "--only-dog1-seeds" in sys.argv:
+        torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+        from dd4ml.utility import get_lssr1_tr_hparams
+        hp = get_lssr1_tr_hparams(apts_cfg("lssr1_tr", "lssr1_tr", True, True, 3))
+        hp["sync"] = False
+        for j, seed in enumerate((2001, 2002, 2003), start=1):
+            run_plain(f"lssr1_so_dog1_s{j}", lambda m, hp=hp: LSSR1_TR(m.parameters(), **hp), 30, data_seed=seed)
+        return
     if "--only-ws8" in sys.argv:
         torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
         run_apts("apts_d_tr_fo_ws8", "apts_d", 8, "tr", "tr", False, False, 3, 8, port=29651)
@@ -587,6 +595,9 @@ def main():
         hp = get_lssr1_tr_hparams(apts_cfg("lssr1_tr", "lssr1_tr", True, dog, 3))
         hp["sync"] = False
         run_plain(f"lssr1_so_dog{int(dog)}", lambda m, hp=hp: LSSR1_TR(m.parameters(), **hp), 30)
+        if dog:
+            for j, seed in enumerate((2001, 2002, 2003), start=1):
+                run_plain(f"lssr1_so_dog1_s{j}", lambda m, hp=hp: LSSR1_TR(m.parameters(), **hp), 30, data_seed=seed)
     hp = get_lssr1_tr_hparams(apts_cfg("lssr1_tr", "lssr1_tr", False, False, 3))
     hp["sync"] = False
     run_plain("lssr1_fo", lambda m: LSSR1_TR(m.parameters(), **hp), 20)

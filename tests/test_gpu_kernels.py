@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from _helpers import load_golden, rel_err
+from _helpers import oracle_memory, sigma_spread, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -102,14 +102,59 @@ def test_second_order_solve(m, dog, delta):
     info = {}
     p_or, pred_or = solve_second_order(g, torch.norm(g), delta, hc, 1e-6, dogleg=dog, eig_sign="canonical", info=info)
     assert {"A": 1, "C": 3}[info["case"]] == obs.last["case"]
-    # typical agreement is ~1e-7; the fp32 reference pipeline itself carries cond(Psi^T Psi)*eps
-    # noise for the delta=100 cases (see tests/test_kspace_host.py), hence the bound
-    assert rel_err(p.cpu(), p_or) < 2e-4
-    assert float(pred) == pytest.approx(float(pred_or), rel=2e-3, abs=1e-6)
-    same_start = (not int(gold[key + "_newton"])) or \
-        abs(float(gold[key + "_x0"]) - obs.last["sigma0"]) <= 1e-3 * abs(obs.last["sigma0"]) + 1e-7
-    if same_start:      # the reference's sigma_0 did not depend on LAPACK's eigenvector signs
-        assert rel_err(p.cpu(), gold[key + "_p"]) < 2e-4
+    # Yardstick: the float64 evaluation of the reference algorithm on the same pairs.  The reference's own
+    # float32 result (the golden) sits e_ref away from it: <= 4e-7 on 19 of these 24 solves and 2e-6 ... 1.7e-4
+    # on the delta = 100 ones (cond(Psi^T Psi) * eps of its float32 LAPACK pipeline).  Stated bound: the CUDA
+    # path is within 1e-5 of the REFERENCE GOLDEN wherever the reference itself is that accurate, and within
+    # the reference's own float32 error elsewhere.  None of the 24 solves is eigenvector-sign sensitive
+    # (tests/test_oracle_golden.py::test_sign_sensitivity_census_of_the_reference_goldens).
+    hc64 = oracle_memory(torch.stack(hc.S, 1), torch.stack(hc.Y, 1), float(hc.gamma), torch.float64)
+    p64, pred64 = solve_second_order(g.double(), torch.norm(g.double()), delta, hc64, 1e-6, dogleg=dog, eig_sign="canonical")
+    e_ref = rel_err(gold[key + "_p"], p64)
+    assert sigma_spread(info, delta, float(hc.gamma)) <= 1e-6
+    assert rel_err(p.cpu(), gold[key + "_p"]) < 1e-5 + 1.5 * e_ref, (e_ref, rel_err(p.cpu(), gold[key + "_p"]))
+    assert rel_err(p.cpu(), p_or) < 1e-5 + 1.5 * e_ref
+    pe_ref = abs(float(gold[key + "_pred"]) - float(pred64)) / max(abs(float(pred64)), 1e-12)
+    assert float(pred) == pytest.approx(float(gold[key + "_pred"]), rel=1e-5 + 1.5 * pe_ref, abs=1e-9)
+
+
+GOLDEN_TRAJ = ("tr_so", "tr_so_dogleg", "lssr1_so_dog0", "lssr1_so_dog1", "lssr1_paper")
+
+
+@pytest.mark.parametrize("name", GOLDEN_TRAJ)
+def test_solves_recorded_inside_reference_trajectories(name):
+    """The 8 sub-problem solves the unmodified reference performed first in each second-order trajectory
+    golden (inputs g, S, Y, gamma, delta and output p, pred recorded by gen_golden.SolveRecorder), re-solved
+    on the GPU from the recorded inputs.  Per solve: (i) sign-insensitive (39 of 40): compared with the
+    REFERENCE's p at 1e-5 + 1.5 e_ref, e_ref = the reference's own distance from the float64 evaluation of its
+    algorithm (<= 1e-5 on 31 solves, up to 8e-3 on the ill-conditioned ones); (ii) the one sign-sensitive
+    solve (lssr1_so_dog1 #6): compared with the oracle under this implementation's documented sign
+    convention, same bound."""
+    from _helpers import golden_solves
+    obs = dd4ml_b200.OBS()
+    n_sens = 0
+    for i, r in enumerate(golden_solves(name)):
+        g = torch.from_numpy(r["g"])
+        delta, dog, tol, gamma = float(r["delta"]), bool(int(r["dogleg"])), float(r["tol"]), float(r["gamma"])
+        k = r["S"].shape[1]
+        h = LSR1(gamma=gamma, memory_length=max(k, 1), tol=tol, device=DEV)
+        h.set_memory(torch.from_numpy(r["S"]), torch.from_numpy(r["Y"]), gamma)
+        p, pred = solve_tr_second_order(g.to(DEV), torch.norm(g), delta, h, obs, tol, dogleg=dog)
+        info = {}
+        p_can, pred_can = solve_second_order(g, torch.norm(g), delta, oracle_memory(r["S"], r["Y"], gamma), tol,
+                                             dogleg=dog, eig_sign="canonical", info=info)
+        p64, _ = solve_second_order(g.double(), torch.norm(g.double()), delta,
+                                    oracle_memory(r["S"], r["Y"], gamma, torch.float64), tol, dogleg=dog,
+                                    eig_sign="canonical")
+        sens = sigma_spread(info, delta, gamma) > 1e-6
+        n_sens += sens
+        target = p_can if sens else torch.from_numpy(r["p"])
+        e_ref = rel_err(target, p64)
+        err = rel_err(p.cpu(), target)
+        print(f"{name} solve {i}: k={k} case={info['case']} sensitive={sens} e_ref={e_ref:.1e} gpu-vs-{'oracle' if sens else 'reference'}={err:.1e}")
+        assert err < 1e-5 + 1.5 * e_ref, (name, i, err, e_ref)
+        assert {"A": 1, "C": 3}[info["case"]] == obs.last["case"]
+    assert n_sens == (1 if name == "lssr1_so_dog1" else 0)
 
 
 def test_second_order_well_conditioned_within_1e5():

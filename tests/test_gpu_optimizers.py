@@ -169,6 +169,9 @@ def test_flat_views_survive_set_to_none():
     ("lssr1_fo", dict(glob_second_order=False)),
     ("lssr1_so_dog0", dict(glob_second_order=True, glob_dogleg=False)),
     ("lssr1_so_dog1", dict(glob_second_order=True, glob_dogleg=True)),
+    ("lssr1_so_dog1_s1", dict(glob_second_order=True, glob_dogleg=True)),
+    ("lssr1_so_dog1_s2", dict(glob_second_order=True, glob_dogleg=True)),
+    ("lssr1_so_dog1_s3", dict(glob_second_order=True, glob_dogleg=True)),
     ("lssr1_paper", dict(glob_second_order=True, paper_tr_update=True))])
 def test_lssr1_matches_oracle_and_reference(name, kw):
     g = load_golden(name)
@@ -207,8 +210,31 @@ def test_lssr1_matches_oracle_and_reference(name, kw):
         d, br = branch_distance(losses, orun, 6, seeds=16)
         print(f"{name}: distance to the closest oracle branch over 6 steps: {d:.2e}")
         assert d < 1e-3, (losses[:6], br)
-        np.testing.assert_allclose(losses[:2], g["loss"][:2], rtol=5e-4)
         assert losses[-1] < losses[0]
+        # Against the REFERENCE itself: the literal (LAPACK-sign) oracle reproduces the golden bit for bit, so
+        # replaying it tells which solve of THIS trajectory is the first whose sigma* depends on the
+        # eigenvector signs LAPACK happened to return (tests/_helpers.sigma_spread).  Up to that step the GPU
+        # run must be on the reference's trajectory: radii identical, losses to 5e-4 (float32 model on GPU vs
+        # CPU) -- unless a discrete decision (pair acceptance, Wolfe / zoom exit) flipped earlier under that
+        # rounding, which shows as a radius mismatch and is reported, not tolerated, for the first 4 steps.
+        from _helpers import sigma_spread
+        ref = oracle.LSSR1TROracle(**ohp, eig_sign="lapack")
+        rw = torch.from_numpy(g["w0"]).clone()
+        rfg = make_fg(FFNN(IN_F, HID, OUT), X, Y)
+        first_sens = int(g["steps"])
+        for i in range(int(g["steps"])):
+            ref.step(rfg, rw)
+            info = ref.trace[-1].get("obs") or {}
+            if "Lambda" in info and sigma_spread(info, ref.trace[-1]["delta_in"]) > 1e-6:
+                first_sens = i
+                break
+        same = 0
+        while same < int(g["steps"]) and abs(deltas[same] - float(g["delta"][same])) <= 1e-9 * float(g["delta"][same]) \
+                and abs(losses[same] - float(g["loss"][same])) <= 5e-4 * abs(float(g["loss"][same])):
+            same += 1
+        print(f"{name}: first sign-sensitive solve of the reference trajectory at step {first_sens}; GPU run on the "
+              f"reference trajectory (radii identical, losses to 5e-4) for the first {same} steps")
+        assert same >= min(first_sens, 4), (same, first_sens)
 
 
 # ------------------------------------------------------------------------------ APTS (single rank)
@@ -381,10 +407,11 @@ def test_tr_float64_parameters_fp32_gradient_buffer(so):
     assert d < 1e-4, (losses, br)
 
 
-def test_lssr1_strict_read_order_matches_reference(monkeypatch):
-    """DD4ML_B200_DEVICE_CONTROL=0: the convergence test is read before the first line-search
-    evaluation (the reference's order of operations, lssr1_tr.py:509); default folds the two reads."""
-    monkeypatch.setenv("DD4ML_B200_DEVICE_CONTROL", "0")
+def test_lssr1_strict_read_order_matches_reference():
+    """A stand-alone LSSR1_TR reads the convergence test before the first line-search evaluation (the
+    reference's order of operations and closure-call sequence, lssr1_tr.py:509); the speculative first
+    evaluation is opt-in (DD4ML_B200_SPECULATIVE=1) or enabled by the APTS classes for side-effect-free
+    models only."""
     g = load_golden("lssr1_fo")
     X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
     model = gpu_model(g)
@@ -525,3 +552,33 @@ def test_device_control_surfaces_inner_numerical_failures():
     YY[order[1], order[1]] = rep.YY[order[1] * ms + order[1]]
     h.ds.set_array("YY", YY.ravel())
     opt.step(X, Y)
+
+
+@pytest.mark.parametrize("stochastic", [False, True])
+def test_speculative_evaluation_never_changes_the_closure_call_sequence_of_side_effect_models(stochastic, monkeypatch):
+    """SURVEY 7.3 #5 / apts_base.py:245-318: with dropout (or BatchNorm) in the model the APTS classes keep
+    the reference's exact evaluation sequence -- speculation is switched off and the number of forward
+    passes per outer iteration equals the oracle's evaluation count; for a side-effect-free model it is on."""
+    monkeypatch.setenv("DD4ML_B200_CUDA_GRAPHS", "0")           # count eager forward passes
+    g = load_golden("apts_d_tr_fo_ws1")
+    X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
+    base = FFNN(IN_F, HID, OUT)
+    set_flat(base, torch.from_numpy(g["w0"]))
+    if stochastic:
+        base.head = nn.Sequential(nn.Dropout(0.0 + 1e-12), base.head)      # p > 0: counts as a side effect, numerically inert
+    model = base.to(DEV)
+    opt = _apts("d", model, "lssr1_tr", "lssr1_tr", cfg(), foc=True)
+    assert APTS_D.closure_has_side_effects(model) == stochastic
+    assert opt.glob_opt.speculative_first_eval == (not stochastic) == opt.loc_opt.speculative_first_eval
+    fgs = [make_fg(FFNN(IN_F, HID, OUT), torch.from_numpy(g["X"]), torch.from_numpy(g["Y"]))]
+    oopt = oracle.APTSDOracle(torch.from_numpy(g["w0"]), 1, "lssr1_tr",
+                              oracle.lssr1_hparams(0.1, 0.01, 1.0, second_order=False), "lssr1_tr",
+                              oracle.lssr1_loc_hparams(0.1, 0.01, 1.0, 1, second_order=False),
+                              **oracle.apts_hparams(0.1, 0.01, 1.0), glob_pass=True, foc=True, norm_type=2,
+                              max_loc_iters=3, max_glob_iters=1, tol=1e-6)
+    for _ in range(4):
+        loss = float(opt.step(X, Y))
+        oloss = float(oopt.step(fgs))
+        assert loss == pytest.approx(oloss, rel=2e-4)
+        # reference counter: global evaluations + local evaluations (apts_base.py:259,314,413-417)
+        assert opt.grad_evals == pytest.approx(oopt.grad_evals, abs=1e-9)
