@@ -340,11 +340,12 @@ def measure(job, args, world, device, flush, rank, local, full=True):
     opt = job.opt
     batch = job.upload(job.host_batch)
     torch.cuda.synchronize(device)
-    losses, evals = [], []
+    losses, evals, loc_evals = [], [], []
 
     def step_resident(i):
         losses.append(job.step(batch))
         evals.append(float(getattr(opt, "grad_evals", 0.0)))
+        loc_evals.append(float(getattr(opt, "loc_grad_evals", 0.0)))     # THIS rank's local evaluations
 
     for i in range(args.warmup):
         step_resident(i)
@@ -352,9 +353,10 @@ def measure(job, args, world, device, flush, rank, local, full=True):
     if rank == 0 and full:
         sampler.start()
     l0, s0 = lib.launches, job.sync_count()
-    del evals[:]
+    del evals[:], loc_evals[:]
     ms, wall = timed_region(step_resident, args.steps, world, device, flush)
     evals_per_step = sum(evals) / max(len(evals), 1)
+    loc_evals_per_step = sum(loc_evals) / max(len(loc_evals), 1)
     launches = lib.launches - l0
     host_syncs = (job.sync_count() - s0) / args.steps
     clocks = sampler.stop() if (rank == 0 and full) else None
@@ -410,9 +412,25 @@ def measure(job, args, world, device, flush, rank, local, full=True):
                         "achieved_gbs": None if not byt else byt / (sum(ts) / len(ts)) / 1e6}
     prof_step_ms = sum(a.elapsed_time(b) for a, b in ev_step) / nprof
     closure_ms = sum(a.elapsed_time(b) for a, b in cl) / nprof if cl else None
-    comm_ts = [a.elapsed_time(b) for a, b, _ in comm]
+    comm_ts = [a.elapsed_time(b) for a, b, k in comm if k > 0]          # NCCL all-reduces
+    comb_ts = [a.elapsed_time(b) for a, b, k in comm if k < 0]          # fused peer-memory combine (+ its barrier)
     own_ms = sum(v["total_ms_per_step"] for v in native.values())
     dominant = max(native, key=lambda k: native[k]["total_ms_per_step"]) if native else "dd4ml_lssr1_begin"
+    # per-rank view (N > 1): the subdomains' local phases take data-dependent numbers of evaluations and
+    # every collective waits for the slowest rank -- the spread below is what the weak-scaling curve pays
+    per_rank = None
+    if world > 1:
+        mine = {"rank": rank, "local_evals_per_step": loc_evals_per_step,
+                "closure_ms_per_step": closure_ms, "closures_per_step": (len(cl) / nprof) if cl else None,
+                "exchange_ms_per_step": (sum(comm_ts) + sum(comb_ts)) / nprof,
+                "own_kernel_ms_per_step": own_ms}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        le = [r["local_evals_per_step"] for r in allr]
+        ex = [r["exchange_ms_per_step"] for r in allr]
+        per_rank = {"local_evals_per_step": {"min": min(le), "mean": sum(le) / world, "max": max(le)},
+                    "exchange_ms_per_step_incl_waiting": {"min": min(ex), "mean": sum(ex) / world, "max": max(ex)},
+                    "ranks": allr}
     res = {
         "metric": spec["metric"], "value": value, "unit": spec["unit"], "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "e2e": e2e, "gpu_launches": launches,
@@ -426,7 +444,13 @@ def measure(job, args, world, device, flush, rank, local, full=True):
             "per_step": len(comm_ts) / nprof, "avg_us": 1e3 * sum(comm_ts) / len(comm_ts),
             "median_us": 1e3 * statistics.median(comm_ts), "max_us": 1e3 * max(comm_ts),
             "total_ms_per_step": sum(comm_ts) / nprof, "payload_elems": max(c[2] for c in comm)},
-        "wall_ms_per_step": wall * 1e3 / args.steps,
+        "p2p_combine": None if not comb_ts else {
+            "per_step": len(comb_ts) / nprof, "avg_us": 1e3 * sum(comb_ts) / len(comb_ts),
+            "median_us": 1e3 * statistics.median(comb_ts), "max_us": 1e3 * max(comb_ts),
+            "what": "device barrier + ONE kernel: sum of all subdomains' packed steps over NVLink peer memory, "
+                    "applied to w0 (replaces pack -> ncclAllReduce -> apts_trial)"},
+        "exchange": getattr(opt, "_p2p_note", None),
+        "wall_ms_per_step": wall * 1e3 / args.steps, "per_rank": per_rank,
         "first_loss": float(losses[0]), "final_loss": float(losses[-1]),
         "roofline_native": {"n": n, "k": kmem, "dominant": dominant, "own_kernel_ms_per_step": own_ms,
                             "own_kernel_share_of_step": own_ms / prof_step_ms, "kernels": native},
@@ -588,6 +612,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other configs / teacher labels")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--teacher-extra", action="store_true",
+                    help="also time the same workload with teacher labels (the N >= 2 stall at ln 10 is the same)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -626,7 +652,7 @@ def main():
 
     # ---- equal-work scaling diagnostic: the same workload with learnable (teacher) labels
     teacher = None
-    if args.config == "ffnn_apts_d" and args.labels == "random" and not args.no_extra:
+    if args.config == "ffnn_apts_d" and args.labels == "random" and args.teacher_extra:
         tjob = build_job("ffnn_apts_d", device, world, rank, labels="teacher")
         targs = argparse.Namespace(steps=min(args.steps, 20), warmup=3)
         tres, _, _ = measure(tjob, targs, world, device, flush, rank, local, full=False)
@@ -695,7 +721,8 @@ def main():
         "outer_iters_per_sec": args.steps / (res["ms_per_step"] * args.steps / 1e3),
         **{k: res[k] for k in ("wall_ms_per_step", "e2e", "gpu_launches", "host_syncs_per_step", "grad_evals_per_step",
                                "ms_per_grad_eval", "closure_ms_per_step", "closures_per_step",
-                               "optimizer_side_ms_per_step", "profiled_ms_per_step", "allreduce")},
+                               "optimizer_side_ms_per_step", "profiled_ms_per_step", "allreduce", "p2p_combine",
+                               "exchange", "per_rank")},
         "clocks": clocks, "roofline": roofline, "roofline_native": res["roofline_native"],
         "roofline_sweep": sweep, "cpu_baseline": cpu, "parity_check": parity, "teacher_labels": teacher,
         "other_configs": others,

@@ -73,6 +73,7 @@ _SIGS = {
     "dd4ml_apts_foc": ([c_void_p] * 7 + [c_int, c_double, c_int64, c_int, c_int, c_void_p], c_int),
     "dd4ml_apts_pack": ([c_void_p] * 5 + [c_int, c_double, c_double, c_int64, c_int, c_int, c_void_p], c_int),
     "dd4ml_apts_trial": ([c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_int64, c_int, c_int, c_void_p], c_int),
+    "dd4ml_apts_combine": ([c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_double, c_void_p, c_int64, c_int, c_int, c_void_p], c_int),
     "dd4ml_tradam_moments": ([c_void_p] * 5 + [c_double] * 6 + [c_int, c_int64, c_int, c_void_p], c_int),
     "dd4ml_tradam_apply": ([c_void_p] * 6 + [c_double] * 3 + [c_int64, c_int, c_int, c_void_p], c_int),
     "dd4ml_apts_control": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int] + [c_void_p] * 6 + [c_int64, c_int, c_int, c_void_p], c_int),

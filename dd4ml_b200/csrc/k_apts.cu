@@ -133,6 +133,55 @@ struct AptsTrialOp {
     __device__ void finalize(const double*, dd4ml_state*) {}
 };
 
+// The additive-Schwarz combination fused with its exchange (apts_d.py:139-150 + apts_base.py:445): every
+// rank reads the packed steps [w_loc - w0 || pred || evals] of ALL subdomains straight out of its peers'
+// HBM over NVLink (symmetric-memory buffers, one per rank), sums them in rank order -- fixed order and
+// float64 accumulation, so every rank forms bit-identical sums -- and applies w = w0 + scale * sum in the
+// same pass.  Replaces pack -> ncclAllReduce -> apts_trial (two extra passes over the n-vector and the
+// collective's launch + protocol latency); the caller brackets it with a device-side barrier on the
+// symmetric-memory signal pads.
+constexpr int MAX_PEERS = 16;
+template <class BT> struct PeerTable { const BT* buf[MAX_PEERS]; int n; };
+
+template <class WT, class BT>
+struct CombineOp {
+    static constexpr int NRED = 0;
+    __host__ __device__ static constexpr bool is_max(int) { return false; }
+    WT* w;
+    const WT* w0;
+    PeerTable<BT> peers;
+    BT* tail;             // [sum of pred, sum of evals]
+    double scale;
+    int64_t n;
+    __device__ dd4ml_state* state() const { return nullptr; }
+    __device__ void setup() {
+        if (blockIdx.x == 0 && threadIdx.x < 2) {
+            double s = 0.0;
+            for (int r = 0; r < peers.n; ++r) s += (double)peers.buf[r][n + threadIdx.x];
+            tail[threadIdx.x] = (BT)s;
+        }
+    }
+    __device__ bool active() const { return true; }
+    template <int V>
+    __device__ __forceinline__ void body(int64_t i, double*) {
+        double a[V], s[V];
+        ld_ro<V, WT>(w0, i, a);
+#pragma unroll
+        for (int e = 0; e < V; ++e) s[e] = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < peers.n; ++r) {
+            double b[V];
+            ld_rw<V, BT>(peers.buf[r], i, b);      // peer memory: plain (coherent) loads, not the read-only path
+#pragma unroll
+            for (int e = 0; e < V; ++e) s[e] += b[e];
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) a[e] += rnd<BT>(rnd<BT>(s[e]) * scale);
+        st_v<V, WT>(w, i, a);
+    }
+    __device__ void finalize(const double*, dd4ml_state*) {}
+};
+
 template <class VT, class WT>
 struct ControlOp {
     static constexpr int NRED = 2;
@@ -228,6 +277,30 @@ int dd4ml_apts_trial(void* w, const void* w0, const void* buf, int mode, double 
     if (wt == 0 && bt == 0) { AptsTrialOp<float, float> op{(float*)w, (const float*)w0, buf, mode, scale, clampv}; return launch(op, n, vec, nullptr, 4, s); }
     if (wt == 1 && bt == 1) { AptsTrialOp<double, double> op{(double*)w, (const double*)w0, buf, mode, scale, clampv}; return launch(op, n, vec, nullptr, 4, s); }
     if (wt == 1 && bt == 0) { AptsTrialOp<double, float> op{(double*)w, (const double*)w0, buf, mode, scale, clampv}; return launch(op, n, vec, nullptr, 4, s); }
+    return DD4ML_E_DTYPE;
+}
+
+int dd4ml_apts_combine(void* w, const void* w0, const void* const* peer_bufs, int nranks, double scale,
+                       void* tail_out, int64_t n, int wt, int bt, void* stream) {
+    if (!w || !w0 || !peer_bufs || !tail_out || nranks < 1 || nranks > MAX_PEERS || n < 0) return DD4ML_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    bool vec = aligned16(w) && aligned16(w0);
+    for (int r = 0; r < nranks; ++r) {
+        if (!peer_bufs[r]) return DD4ML_E_ARG;
+        vec = vec && aligned16(peer_bufs[r]);
+    }
+#define COMBINE(WT, BT)                                                                                   \
+    {                                                                                                     \
+        PeerTable<BT> pt;                                                                                 \
+        pt.n = nranks;                                                                                    \
+        for (int r = 0; r < MAX_PEERS; ++r) pt.buf[r] = r < nranks ? (const BT*)peer_bufs[r] : nullptr;   \
+        CombineOp<WT, BT> op{(WT*)w, (const WT*)w0, pt, (BT*)tail_out, scale, n};                         \
+        return launch(op, n, vec, nullptr, 4, s);                                                         \
+    }
+    if (wt == 0 && bt == 0) COMBINE(float, float)
+    if (wt == 1 && bt == 1) COMBINE(double, double)
+    if (wt == 1 && bt == 0) COMBINE(double, float)
+#undef COMBINE
     return DD4ML_E_DTYPE;
 }
 

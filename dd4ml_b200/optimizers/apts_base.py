@@ -372,16 +372,18 @@ class APTS_Base(Optimizer):
                                closure=self.glob_closure_main if closure is None else closure)
 
     # ------------------------------------------------------------------ control step
-    def _control(self, buf, mode, scale, clampv, f0, pred_ptr, pred_dt, aux_ptr, bt=None):
+    def _control(self, buf, mode, scale, clampv, f0, pred_ptr, pred_dt, aux_ptr, bt=None, pre_applied=False):
         """apts_base.py:432-501 with `pred` supplied (APTS_D / APTS_P).  `buf` holds the combined
-        step (mode 0) or the merged parameters (mode 1).  Returns (loss, grad, delta)."""
+        step (mode 0) or the merged parameters (mode 1); `pre_applied`: the trial point w0 + step is
+        already in place (fused peer-memory combine).  Returns (loss, grad, delta)."""
         b = self._buffers()
         lib, ctl = self._ctl.lib, self._ctl
         n, wt = self._gfs.n, _lib.dt(self._gfs.dtype)
         st = _lib.stream()
         self._push_ctl()
-        lib.apts_trial(_lib.ptr(self._gfs.data), _lib.ptr(b["w0"]), _lib.ptr(buf), mode, float(scale),
-                       float(clampv), n, wt, _lib.dt(self._ctor_dtype if bt is None else bt), st)
+        if not pre_applied:
+            lib.apts_trial(_lib.ptr(self._gfs.data), _lib.ptr(b["w0"]), _lib.ptr(buf), mode, float(scale),
+                           float(clampv), n, wt, _lib.dt(self._ctor_dtype if bt is None else bt), st)
         trial = as_device_scalar(self.glob_closure_main(compute_grad=True), self.device)
         f0 = as_device_scalar(f0, self.device)
         if trial.dtype != f0.dtype:

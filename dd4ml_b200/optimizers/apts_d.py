@@ -59,12 +59,58 @@ class APTS_D(APTS_Base):
             self.glob_opt.delta = min(self.glob_opt.max_delta, self.delta * self.sqrt_n_global)
             self.loc_opt.delta = min(self.loc_opt.max_delta, self.delta * self.sqrt_n_local)
         self._has_buffers = any(True for _ in self.loc_model.buffers())
+        self._setup_p2p_combine()
         self._enable_device_control()
         from ..graphs import GraphedEval
         self._loc_eval = GraphedEval(self.loc_model, self.criterion, self._lfs)
 
     def _comm_dtype(self):
         return self._ctor_dtype
+
+    def _setup_p2p_combine(self):
+        """Symmetric-memory exchange buffers for the fused additive-Schwarz combine (csrc/k_apts.cu
+        CombineOp): every rank's packed step lives in a buffer all ranks of the NVLink domain can load
+        from, double-buffered by outer-iteration parity so one device-side barrier per iteration orders
+        the peers' reads against the next write.  NCCL all-reduce remains the path when symmetric memory
+        is unavailable (no NVLink P2P, non-NCCL backend, DD4ML_B200_P2P_COMBINE=0): the decision is taken
+        collectively so that all ranks use the same exchange."""
+        import ctypes
+        import os
+        self._p2p, self._p2p_note = None, "single subdomain"
+        if not self._distributed:
+            return
+        ok = os.environ.get("DD4ML_B200_P2P_COMBINE", "1") != "0" and dist.get_backend() == "nccl"
+        ws = dist.get_world_size()
+        symm = None
+        if ok:
+            try:
+                import torch.distributed._symmetric_memory as symm      # noqa: F401
+            except Exception as e:  # noqa: BLE001
+                ok, self._p2p_note = False, f"symmetric memory unavailable: {e!r}"
+        flag = torch.tensor([1 if (ok and ws <= 16) else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0:
+            self._p2p_note = self._p2p_note if not ok else "disabled on another rank"
+            if os.environ.get("DD4ML_B200_P2P_COMBINE", "1") == "0":
+                self._p2p_note = "DD4ML_B200_P2P_COMBINE=0"
+            return
+        state = None
+        try:
+            n, dt = self._gfs.n, self._ctor_dtype
+            L = (n + 2 + 3) // 4 * 4
+            t = symm.empty(2 * L, dtype=dt, device=self.device)
+            t.zero_()
+            hdl = symm.rendezvous(t, dist.group.WORLD)
+            es = t.element_size()
+            tables = [(ctypes.c_void_p * ws)(*[int(p) + b * L * es for p in hdl.buffer_ptrs]) for b in (0, 1)]
+            state = dict(t=t, hdl=hdl, L=L, tables=tables, bufs=[t[:n + 2], t[L:L + n + 2]], it=0, ws=ws,
+                         tail=torch.zeros(2, dtype=dt, device=self.device))
+        except Exception as e:  # noqa: BLE001
+            self._p2p_note = f"rendezvous failed: {e!r}"
+        flag = torch.tensor([1 if state is not None else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 1:
+            self._p2p, self._p2p_note = state, "peer-memory combine over symmetric memory"
 
     # ------------------------------------------------------------------ apts_base.py:228-243
     @torch.no_grad()
@@ -144,21 +190,36 @@ class APTS_D(APTS_Base):
         loc_loss, _ = self.loc_steps(self.init_loc_loss, self.init_loc_grad)
         loc_loss = as_device_scalar(loc_loss, self.device, self.init_loc_loss.dtype)
 
-        comm = b["comm"]
+        p2p = self._p2p
+        if p2p is not None:
+            par = p2p["it"] & 1
+            p2p["it"] += 1
+            comm = p2p["bufs"][par]
+        else:
+            comm = b["comm"]
         lib.apts_pack(_lib.ptr(comm), _lib.ptr(self._lfs.data), _lib.ptr(b["w0"]), _lib.ptr(self.init_loc_loss),
                       _lib.ptr(loc_loss), _lib.dt(self.init_loc_loss.dtype),
                       float(weight) if self.nr_models > 1 else 1.0, float(self.loc_grad_evals), n, wt,
                       _lib.dt(comm.dtype), st)
         scale = 1.0
-        if self._distributed:
-            apts_base.all_reduce(comm, dist.ReduceOp.SUM)             # additive Schwarz (apts_d.py:144)
-            if self.norm_type == math.inf:
-                scale = 1.0 / self.nr_models
+        if self._distributed and self.norm_type == math.inf:
+            scale = 1.0 / self.nr_models
         use(glob_io, on_glob)
         es = comm.element_size()
-        loss, grad, delta, evals_sum, gn = self._control(
-            comm, 0, scale, 0.0, self.init_glob_loss, comm.data_ptr() + n * es, _lib.dt(comm.dtype),
-            comm.data_ptr() + (n + 1) * es)
+        if p2p is not None:
+            # additive Schwarz (apts_d.py:144) + w = w0 + step (apts_base.py:445) in ONE kernel over NVLink
+            # peer memory; the barrier orders it behind every rank's pack kernel
+            self._p2p_exchange(comm, p2p, par, scale, b, n, wt, st)
+            tail = p2p["tail"]
+            loss, grad, delta, evals_sum, gn = self._control(
+                None, 0, scale, 0.0, self.init_glob_loss, tail.data_ptr(), _lib.dt(tail.dtype),
+                tail.data_ptr() + es, pre_applied=True)
+        else:
+            if self._distributed:
+                apts_base.all_reduce(comm, dist.ReduceOp.SUM)         # additive Schwarz (apts_d.py:144)
+            loss, grad, delta, evals_sum, gn = self._control(
+                comm, 0, scale, 0.0, self.init_glob_loss, comm.data_ptr() + n * es, _lib.dt(comm.dtype),
+                comm.data_ptr() + (n + 1) * es)
         if self._device_control:
             self._link(self.glob_opt._ds, self._ctl)                  # glob_opt.delta <- control delta
             self.glob_opt._delta_stale = True
@@ -174,6 +235,18 @@ class APTS_D(APTS_Base):
             self.sync_glob_to_loc()
         self.grad_evals += evals_sum / (self.nr_models if self._distributed else 1)   # apts_base.py:413-417
         return loss
+
+    def _p2p_exchange(self, comm, p2p, par, scale, b, n, wt, st):
+        lib = self._ctl.lib
+        if apts_base.COMM_PROF is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        p2p["hdl"].barrier(channel=0)
+        lib.apts_combine(_lib.ptr(self._gfs.data), _lib.ptr(b["w0"]), p2p["tables"][par], p2p["ws"], float(scale),
+                         _lib.ptr(p2p["tail"]), n, wt, _lib.dt(comm.dtype), st)
+        if apts_base.COMM_PROF is not None:
+            e1.record()
+            apts_base.COMM_PROF.append((e0, e1, -(n + 2)))      # negative payload marks the fused combine
 
     def step(self, inputs, labels, inputs_d=None, labels_d=None, hNk=None):
         self.inputs_d, self.labels_d, self.hNk = inputs_d, labels_d, hNk

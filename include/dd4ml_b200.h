@@ -120,6 +120,15 @@ int dd4ml_apts_pack(void* buf, const void* w_loc, const void* w0, const void* lo
                     int bt, void* stream);
 int dd4ml_apts_trial(void* w, const void* w0, const void* buf, int mode, double scale,
                      double clampv, int64_t n, int wt, int bt, void* stream);
+/* combine: the additive-Schwarz combination fused with its exchange over NVLink peer memory
+ *           (apts_d.py:139-150 all-reduce of [step || pred] + apts_base.py:445 w = w0 + step): `peer_bufs`
+ *           is a HOST array of `nranks` DEVICE pointers to the packed buffers (dtype bt, n+2 elements,
+ *           written by dd4ml_apts_pack) of all ranks in rank order -- symmetric-memory / P2P-mapped
+ *           addresses.  w = w0 + scale * sum_r buf_r[0:n] (rank-ordered float64 accumulation: identical
+ *           on every rank), tail_out[0:2] (dtype bt) = sum_r buf_r[n:n+2].  The caller orders it against
+ *           the peers' pack kernels with a device-side barrier.  Replaces pack -> ncclAllReduce -> trial. */
+int dd4ml_apts_combine(void* w, const void* w0, const void* const* peer_bufs, int nranks, double scale,
+                       void* tail_out, int64_t n, int wt, int bt, void* stream);
 int dd4ml_apts_control(double* state, double* ws, const void* f0, const void* ftrial, int lt,
                        const void* pred, int pt, void* w, const void* w0, void* g0, const void* G,
                        void* loss_out, const void* aux, int64_t n, int vt, int wt, void* stream);

