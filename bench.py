@@ -265,7 +265,7 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
     loss = torch.tensor(1.0, device=device)
     st = _lib.stream()
     calls = {
-        "dd4ml_lssr1_begin": lambda: lib.lssr1_begin(ds.sp, ds.wp, w.data_ptr(), old_w.data_ptr(), gv.data_ptr(),
+        "dd4ml_lssr1_begin": lambda: lib.lssr1_begin(ds.sp, ds.wp, w.data_ptr(), old_w.data_ptr(), old_w.data_ptr(), gv.data_ptr(), prev_g.data_ptr(),
                                                      prev_g.data_ptr(), 1, h.S_ptr, h.Y_ptr, loss.data_ptr(), 0, n,
                                                      h.ld, 0, 0, 0, k, -1.0, 0.0, 0.0, st),
         "dd4ml_tr_propose": lambda: lib.tr_propose(ds.sp, ds.wp, gv.data_ptr(), h.S_ptr, h.Y_ptr, n, h.ld, 0, 0, 1, k, st),

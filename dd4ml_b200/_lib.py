@@ -66,7 +66,7 @@ _SIGS = {
     "dd4ml_state_link": ([c_void_p, c_int, c_void_p, c_int, c_double, c_double, c_double, c_void_p], c_int),
     "dd4ml_lsr1_update": ([c_void_p] * 6 + [c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
     "dd4ml_lsr1_B": ([c_void_p] * 6 + [c_int64, c_int64, c_int, c_int, c_int, c_void_p], c_int),
-    "dd4ml_lssr1_begin": ([c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_void_p], c_int),
+    "dd4ml_lssr1_begin": ([c_void_p] * 8 + [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_double, c_double, c_double, c_void_p], c_int),
     "dd4ml_lssr1_trial": ([c_void_p, c_void_p, c_void_p, c_double, c_int64, c_int, c_int, c_void_p], c_int),
     "dd4ml_lssr1_eval": ([c_void_p] * 6 + [c_int, c_int64, c_int, c_void_p], c_int),
     "dd4ml_apts_residual": ([c_void_p] * 5 + [c_int64, c_int, c_void_p], c_int),

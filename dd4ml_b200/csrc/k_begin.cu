@@ -12,9 +12,11 @@ struct LssrBeginOp {
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
     const WT* w;
-    WT* old_w;
-    const VT* g;
-    VT* prev_g;
+    const WT* old_w;      // previous iterate / gradient: read ...
+    WT* old_w_out;        // ... and written to a second buffer: the reference keeps old_wk / prev_grad when
+    const VT* g;          // ||g|| <= tol (it returns before storing them, lssr1_tr.py:509-526), which is only
+    const VT* prev_g;     // known after this pass -- the host swaps the buffers unless the step converged
+    VT* prev_g_out;
     HT* S;
     HT* Y;
     int64_t ld;
@@ -96,8 +98,8 @@ struct LssrBeginOp {
             st_v<V, HT>(S + (int64_t)spare * ld, i, sv);
             st_v<V, HT>(Y + (int64_t)spare * ld, i, yv);
         }
-        st_v<V, WT>(old_w, i, wv);
-        st_v<V, VT>(prev_g, i, gv);
+        st_v<V, WT>(old_w_out, i, wv);
+        st_v<V, VT>(prev_g_out, i, gv);
     }
     __device__ void finalize(const double* s, dd4ml_state* t) {   // chain + solve: k-space kernel (KT_BEGIN)
         if (rad[0] >= 0.0) { t->delta[0] = rad[0]; t->min_delta[0] = rad[1]; t->max_delta[0] = rad[2]; }
@@ -125,13 +127,14 @@ struct LssrBeginOp {
 
 namespace {
 template <class HT, class VT, class WT>
-int begin_t(double* state, double* ws, const void* w, void* old_w, const void* g, void* prev_g, int has_prev, void* S,
-            void* Y, const void* loss, int lt, int64_t n, int64_t ld, int kcap, bool vec, double delta, double min_delta,
-            double max_delta, cudaStream_t s) {
+int begin_t(double* state, double* ws, const void* w, const void* old_w, void* old_w_out, const void* g,
+            const void* prev_g, void* prev_g_out, int has_prev, void* S, void* Y, const void* loss, int lt, int64_t n,
+            int64_t ld, int kcap, bool vec, double delta, double min_delta, double max_delta, cudaStream_t s) {
     constexpr bool FAST = sizeof(HT) == 4 && sizeof(VT) == 4 && sizeof(WT) == 4;
     auto run = [&](auto kc) {
         constexpr int K = decltype(kc)::value;
-        LssrBeginOp<HT, VT, WT, K> op{(dd4ml_state*)state, (const WT*)w, (WT*)old_w, (const VT*)g, (VT*)prev_g,
+        LssrBeginOp<HT, VT, WT, K> op{(dd4ml_state*)state, (const WT*)w, (const WT*)old_w, (WT*)old_w_out,
+                                      (const VT*)g, (const VT*)prev_g, (VT*)prev_g_out,
                                       (HT*)S, (HT*)Y, ld, has_prev, loss, lt, {delta, min_delta, max_delta}};
         return launch_sel<FAST>(op, n, vec, ws, K <= 4 ? 2 : 1,
                                 TILE * (int)(2 * sizeof(WT) + 2 * sizeof(VT) + 2 * K * sizeof(HT)), true, s);
@@ -140,20 +143,21 @@ int begin_t(double* state, double* ws, const void* w, void* old_w, const void* g
 }
 }  // namespace
 
-extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void* old_w, const void* g,
-                                 void* prev_g, int has_prev, void* S, void* Y, const void* loss, int lt,
-                                 int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, double delta,
-                                 double min_delta, double max_delta, void* stream) {
-    if (!state || !ws || !w || !old_w || !g || !prev_g || !S || !Y || !loss || n < 0 || kcap > DD4ML_MAXM)
+extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, const void* old_w, void* old_w_out,
+                                 const void* g, const void* prev_g, void* prev_g_out, int has_prev, void* S,
+                                 void* Y, const void* loss, int lt, int64_t n, int64_t ld, int vt, int ht, int wt,
+                                 int kcap, double delta, double min_delta, double max_delta, void* stream) {
+    if (!state || !ws || !w || !old_w || !old_w_out || !g || !prev_g || !prev_g_out || !S || !Y || !loss || n < 0 ||
+        kcap > DD4ML_MAXM)
         return DD4ML_E_ARG;
     if (lt != 0 && lt != 1) return DD4ML_E_DTYPE;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool vec = aligned16(w) && aligned16(old_w) && aligned16(g) && aligned16(prev_g) && aligned16(S) &&
-                     aligned16(Y) && ld % 4 == 0;
+    const bool vec = aligned16(w) && aligned16(old_w) && aligned16(old_w_out) && aligned16(g) && aligned16(prev_g) &&
+                     aligned16(prev_g_out) && aligned16(S) && aligned16(Y) && ld % 4 == 0;
     int rc = DD4ML_E_DTYPE;
 #define CALL(HT, VT, WT) \
-    rc = begin_t<HT, VT, WT>(state, ws, w, old_w, g, prev_g, has_prev, S, Y, loss, lt, n, ld, kcap, vec, delta, \
-                             min_delta, max_delta, s);
+    rc = begin_t<HT, VT, WT>(state, ws, w, old_w, old_w_out, g, prev_g, prev_g_out, has_prev, S, Y, loss, lt, n, ld, \
+                             kcap, vec, delta, min_delta, max_delta, s);
     DT_SWITCH3_RC(ht, vt, wt, CALL)
 #undef CALL
     if (rc) return rc;

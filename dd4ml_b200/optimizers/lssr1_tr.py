@@ -147,10 +147,14 @@ class LSSR1_TR(Optimizer):
             n, dev, wt = self._fs.n, self._fs.device, self._fs.dtype
             self._bufs = {
                 "p": torch.zeros(n, dtype=vt, device=dev),
-                "old_w": torch.zeros(n, dtype=wt, device=dev),
-                "prev_g": torch.zeros(n, dtype=vt, device=dev),
+                # previous iterate / gradient, double buffered: lssr1_begin reads pair [cur] and writes pair
+                # [1 - cur]; the host adopts the new pair unless the step turned out converged
+                "old_w2": [torch.zeros(n, dtype=wt, device=dev) for _ in range(2)],
+                "prev_g2": [torch.zeros(n, dtype=vt, device=dev) for _ in range(2)],
                 "gs": [torch.zeros(n, dtype=vt, device=dev) for _ in range(3)],
             }
+            self._cur = 0
+            self._bufs["old_w"], self._bufs["prev_g"] = self._bufs["old_w2"][0], self._bufs["prev_g2"][0]
             self._fs_version = self._fs.version
         return self._bufs
 
@@ -320,9 +324,13 @@ class LSSR1_TR(Optimizer):
             if w_in is None:
                 w_in = b["w_round"] = torch.empty_like(self._fs.data)
             w_in.copy_(self._fs.data.to(self._ctor_dtype))
-        lib.lssr1_begin(ds.sp, ds.wp, _lib.ptr(w_in), _lib.ptr(b["old_w"]), _lib.ptr(g),
-                        _lib.ptr(b["prev_g"]), 1 if self._has_prev else 0, h.S_ptr, h.Y_ptr,
+        nxt = 1 - self._cur
+        lib.lssr1_begin(ds.sp, ds.wp, _lib.ptr(w_in), _lib.ptr(b["old_w2"][self._cur]), _lib.ptr(b["old_w2"][nxt]),
+                        _lib.ptr(g), _lib.ptr(b["prev_g2"][self._cur]), _lib.ptr(b["prev_g2"][nxt]),
+                        1 if self._has_prev else 0, h.S_ptr, h.Y_ptr,
                         _lib.ptr(loss_t), _lib.dt(loss_t.dtype), n, h.ld, vtc, htc, wtc, self.mem_length, *rad, st)
+        prev_pair = (b["old_w"], b["prev_g"])
+        b["old_w"], b["prev_g"] = b["old_w2"][nxt], b["prev_g2"][nxt]      # w_k: the base of every trial point
         # The first trial point of the line search is w_k + 1.0 p (alpha_max / 2, lssr1_tr.py:397): when
         # it is evaluated speculatively, the direction kernel applies it on the way (w += p) instead
         # of a separate trial launch.  (begin has just stored old_w = w_k, so w + p == old_w + 1.0 p.)
@@ -341,9 +349,11 @@ class LSSR1_TR(Optimizer):
             self.last_grad_norm, self.last_grad_inf = rep.gn, rep.ginf
             if pre is not None:                                     # undo the speculative trial point
                 lib.lssr1_trial(_lib.ptr(self._fs.data), _lib.ptr(b["old_w"]), _lib.ptr(b["p"]), 0.0, n, vtc, wtc, st)
-            # the reference returns before touching old_wk / prev_grad; begin has already stored
-            # them, which is equivalent because nothing moves when ||g|| <= tol
+            # the reference returns before touching old_wk / prev_grad (lssr1_tr.py:509-526): keep the
+            # previous pair, the buffers lssr1_begin has just written are scratch again
+            b["old_w"], b["prev_g"] = prev_pair
             return loss, g
+        self._cur = nxt
         self._has_prev = True
         pred = self._f(rep.pred)
         d0 = self._f(rep.dphi0)

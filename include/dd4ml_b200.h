@@ -77,17 +77,19 @@ int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* tri
 
 /* ---- LSSR1_TR.step, optimizers/lssr1_tr.py:493-654 --------------------------------------
  * begin: s = w - old_w, y = g - prev_g (lssr1_tr.py:518-526) with every reduction of the
- *   L-SR1 update chain and of the sub-problem in one pass; old_w <- w, prev_g <- g; the last
- *   CTA runs update_memory, precompute and the sub-problem solve; `loss` (phi_0) is copied into
+ *   L-SR1 update chain and of the sub-problem in one pass; old_w_out <- w, prev_g_out <- g (separate
+ *   buffers: the reference keeps old_wk / prev_grad when ||g|| <= tol, lssr1_tr.py:509-526, which is known
+ *   only after the pass -- the caller swaps the buffer pairs unless state.converged); the k-space
+ *   kernel runs update_memory, precompute and the sub-problem solve; `loss` (phi_0) is copied into
  *   the report block so the host needs no separate read.  delta/min_delta/max_delta: the radius
  *   LSSR1_TR updated on the host after the previous step (lssr1_tr.py:621-652), stored into the
  *   state block before the solve; delta < 0 keeps the block's values.
  * trial: w = base + alpha * p (lssr1_tr.py:262).
  * eval:  deriv = g . p, g_save <- g, loss copied into the report (lssr1_tr.py:265-271). */
-int dd4ml_lssr1_begin(double* state, double* ws, const void* w, void* old_w, const void* g,
-                      void* prev_g, int has_prev, void* S, void* Y, const void* loss, int lt,
-                      int64_t n, int64_t ld, int vt, int ht, int wt, int kcap, double delta,
-                      double min_delta, double max_delta, void* stream);
+int dd4ml_lssr1_begin(double* state, double* ws, const void* w, const void* old_w, void* old_w_out,
+                      const void* g, const void* prev_g, void* prev_g_out, int has_prev, void* S, void* Y,
+                      const void* loss, int lt, int64_t n, int64_t ld, int vt, int ht, int wt, int kcap,
+                      double delta, double min_delta, double max_delta, void* stream);
 int dd4ml_lssr1_trial(void* w, const void* base, const void* p, double alpha, int64_t n, int vt,
                       int wt, void* stream);
 int dd4ml_lssr1_eval(double* state, double* ws, const void* g, const void* p, void* g_save,

@@ -229,7 +229,7 @@ def _oracle_apts_d(w0, glob, loc, so, dog, mem):
                               tol=1e-6, eig_sign="canonical")
 
 
-def _run_apts_d(make_model, X, Y, crit, glob, loc, so, dog, iters):
+def _run_apts_d(make_model, X, Y, crit, glob, loc, so, dog, iters, branch_steps=3):
     torch.manual_seed(7)
     w0 = flat_of(make_model()).clone()
     model = make_model().to(DEV)
@@ -255,9 +255,9 @@ def _run_apts_d(make_model, X, Y, crit, glob, loc, so, dog, iters):
             o = _oracle_apts_d(w0, glob, loc, so, dog, 3)
             fgs = [noisy_fg(cpu_fg(make_model(), X, Y, crit), eps, gen)]
             return [float(o.step(fgs)) for _ in range(4)]
-        d, br = branch_distance(losses, orun, 3, seeds=10)
-        print(f"  distance to the closest oracle branch over 3 outer steps: {d:.2e}")
-        assert d < 5e-3, (losses[:3], br)
+        d, br = branch_distance(losses, orun, branch_steps, seeds=10)
+        print(f"  distance to the closest oracle branch over {branch_steps} outer steps: {d:.2e}")
+        assert d < 5e-3, (losses[:branch_steps], br)
     return losses, olosses
 
 
@@ -313,3 +313,41 @@ def test_c4_gpt_lssr1_tr_top_level():
     print(f"gpt LSSR1_TR first-order: {losses[0]:.5f} -> {losses[-1]:.5f} (oracle {olosses[-1]:.5f})")
     np.testing.assert_allclose(losses, olosses, rtol=1e-3)
     assert rel_err(flat_of(model), ow) < 5e-3
+
+
+# ------------------------------------------------------------------------------ C3 / C4 at their NATIVE sizes
+def _native_cnn():
+    from dd4ml_b200.workloads import SimpleCNN
+    return SimpleCNN(p_drop=0.0)          # n = 620 810; Dropout off so that GPU and CPU evaluate the same function
+
+
+def _native_gpt():
+    from dd4ml_b200.workloads import MiniGPT
+    return MiniGPT(p_drop=0.0)            # gpt-mini, n = 2 719 104 (> 2^20: every vector pass takes the TMA kernels)
+
+
+@pytest.mark.parametrize("glob,loc,so,dog", [("tr", "tr", False, False), ("lssr1_tr", "lssr1_tr", True, True)])
+def test_c3_cnn_native_size_apts_d(glob, loc, so, dog):
+    """BASELINE config 3 at its real size: `simple_cnn` (models/cnn/simple_cnn.py:81-103, n = 620 810) on a
+    CIFAR-10-shape batch, APTS_D against the oracle.  BatchNorm in training mode (batch statistics)."""
+    from dd4ml_b200.workloads import cifar_shape_batch
+    assert sum(p.numel() for p in _native_cnn().parameters()) == 620810
+    X, Y = cifar_shape_batch(64, 11)
+    # second order: cuDNN's float32 convolution gradients differ from the CPU's by ~1e-5 (different summation
+    # order over 64 x 32 x 32 positions), ten times the perturbation the oracle ensemble is built with, and the
+    # loss falls by a factor 2 per outer step here: the first two outer steps (8 inner LSSR1_TR steps, ~18
+    # evaluations) must sit on an oracle branch, the later ones only have to keep descending
+    losses, olosses = _run_apts_d(_native_cnn, X, Y, nn.CrossEntropyLoss(), glob, loc, so, dog, 4,
+                                  branch_steps=2 if so else 3)
+    print(f"native cnn apts_d {glob}/{loc} so={so}: {losses[0]:.5f} -> {losses[-1]:.5f} (oracle {olosses[-1]:.5f})")
+
+
+@pytest.mark.parametrize("glob,loc,so,dog", [("tr", "tr", False, False), ("lssr1_tr", "lssr1_tr", True, True)])
+def test_c4_gpt_mini_native_size_apts_d(glob, loc, so, dog):
+    """BASELINE config 4 at its real size: minGPT `gpt-mini` (models/gpt/base_gpt.py:181, n = 2 719 104, the only
+    config above the 2^20 TMA threshold) on 8 x 128 synthetic tokens, dropout 0, APTS_D against the oracle."""
+    from dd4ml_b200.workloads import token_batch, token_cross_entropy
+    assert sum(p.numel() for p in _native_gpt().parameters()) == 2719104
+    X, Y = token_batch(8, 13)
+    losses, olosses = _run_apts_d(_native_gpt, X, Y, token_cross_entropy, glob, loc, so, dog, 3)
+    print(f"native gpt-mini apts_d {glob}/{loc} so={so}: {losses[0]:.5f} -> {losses[-1]:.5f} (oracle {olosses[-1]:.5f})")

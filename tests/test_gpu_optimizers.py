@@ -582,3 +582,37 @@ def test_speculative_evaluation_never_changes_the_closure_call_sequence_of_side_
         assert loss == pytest.approx(oloss, rel=2e-4)
         # reference counter: global evaluations + local evaluations (apts_base.py:259,314,413-417)
         assert opt.grad_evals == pytest.approx(oopt.grad_evals, abs=1e-9)
+
+
+def test_lssr1_converged_step_keeps_the_previous_iterate_pair():
+    """lssr1_tr.py:509-526: when ||g|| <= tol the reference returns BEFORE it stores old_wk / prev_grad, so
+    the next L-SR1 pair still spans from the last real iterate.  lssr1_begin writes the new pair into a
+    second buffer and the host keeps the old one on a converged step."""
+    g = load_golden("lssr1_so_dog0")
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    model = gpu_model(g)
+    hp = get_lssr1_tr_hparams(cfg(glob_second_order=True, glob_dogleg=False))
+    hp["sync"] = False
+    opt = LSSR1_TR(model.parameters(), **hp)
+    closure = make_closure(opt, model, X.to(DEV), Y.to(DEV))
+    ohp = oracle.lssr1_hparams(0.1, 0.01, 1.0, mem_length=3, second_order=True, dogleg=False)
+    ohp.pop("sync")
+    oopt = oracle.LSSR1TROracle(**ohp, eig_sign="canonical")
+    ofg = make_fg(FFNN(IN_F, HID, OUT), X, Y)
+    ow = torch.from_numpy(g["w0"]).clone()
+    for _ in range(3):
+        loss, _g = opt.step(closure)
+        oloss, _og = oopt.step(ofg, ow)
+    old_w, prev_g = opt._bufs["old_w"].clone(), opt._bufs["prev_g"].clone()
+    n = ow.numel()
+    w_before = flat_of(model).clone()
+    l2, g2 = opt.step(closure, loss=loss.detach(), grad=torch.zeros(n, device=DEV))          # ||g|| = 0 <= tol
+    ol2, og2 = oopt.step(ofg, ow, loss=oloss, grad=torch.zeros(n))
+    assert float(g2.abs().max()) == 0.0 and torch.equal(flat_of(model), w_before)
+    assert torch.equal(opt._bufs["old_w"], old_w) and torch.equal(opt._bufs["prev_g"], prev_g)
+    losses, olosses = [], []
+    for _ in range(3):
+        losses.append(float(opt.step(closure)[0]))
+        olosses.append(float(oopt.step(ofg, ow)[0]))
+    np.testing.assert_allclose(losses, olosses, rtol=1e-3)
+    assert len(opt.hess._S) == len(oopt.hess)

@@ -21,7 +21,7 @@ for n in (217354, 1 << 24):
     loss = torch.tensor(1.0, device=dev)
     A = torch.randn(4096, 4096, device=dev)
     def begin():
-        lib.lssr1_begin(ds.sp, ds.wp, w.data_ptr(), old_w.data_ptr(), gv.data_ptr(), prev_g.data_ptr(), 0,
+        lib.lssr1_begin(ds.sp, ds.wp, w.data_ptr(), old_w.data_ptr(), old_w.data_ptr(), gv.data_ptr(), prev_g.data_ptr(), prev_g.data_ptr(), 0,
                         h.S_ptr, h.Y_ptr, loss.data_ptr(), 0, n, h.ld, 0, 0, 0, k, -1.0, 0.0, 0.0, _lib.stream())
         rep = ds.read()
         return int(rep.cyc_solve), int(rep.cyc_eigh), int(rep.cyc_newton)

@@ -60,7 +60,7 @@ for n in (217354, 2719104):
             return int(rp.cyc_solve), int(rp.cyc_eigh), int(rp.cyc_newton), int(rp.newton_iters), int(rp.k)
 
         def begin():
-            lib.lssr1_begin(ds.sp, ds.wp, w.data_ptr(), old_w.data_ptr(), gv.data_ptr(), prev_g.data_ptr(), 0,
+            lib.lssr1_begin(ds.sp, ds.wp, w.data_ptr(), old_w.data_ptr(), old_w.data_ptr(), gv.data_ptr(), prev_g.data_ptr(), prev_g.data_ptr(), 0,
                             h.S_ptr, h.Y_ptr, loss.data_ptr(), 0, n, h.ld, 0, 0, 0, k, -1.0, 0.0, 0.0, _lib.stream())
 
         def propose():
