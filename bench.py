@@ -283,9 +283,9 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
                       old_w.data_ptr(), p.data_ptr(), w.data_ptr(), h.S_ptr, h.Y_ptr, None, n, h.ld, 0, 0, 0, k, st)
     calls["dd4ml_tr_decide"] = decide
     out = {}
-    for name, fn in calls.items():
-        if name == "dd4ml_tr_apply":
-            lib.tr_propose(ds.sp, ds.wp, gv.data_ptr(), h.S_ptr, h.Y_ptr, n, h.ld, 0, 0, 1, k, st)
+    two_kernel = ("dd4ml_lssr1_begin", "dd4ml_tr_propose", "dd4ml_tr_decide")
+
+    def time_it(fn):
         for _ in range(3):
             fn()
         torch.cuda.synchronize(device)
@@ -295,11 +295,31 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
             fn()
         e1.record()
         torch.cuda.synchronize(device)
-        ms = e0.elapsed_time(e1) / iters
+        return e0.elapsed_time(e1) / iters
+
+    for name, fn in calls.items():
+        if name == "dd4ml_tr_apply":
+            lib.tr_propose(ds.sp, ds.wp, gv.data_ptr(), h.S_ptr, h.Y_ptr, n, h.ld, 0, 0, 1, k, st)
+        ms_entry = time_it(fn)
         kk = int(ds.read().k)
+        ms = ms_entry
+        if name in two_kernel:
+            # these entry points are TWO kernels: the HBM-bound streaming reduction and the one-warp,
+            # latency-bound k-space kernel behind it.  The roofline fraction is the streaming kernel's
+            # (timed alone: k-space kernel switched off through the library's measurement hook); the
+            # whole entry point is reported next to it.
+            state_copy = ds.state.clone()
+            lib.cdll.dd4ml_debug_kspace(0)
+            try:
+                ms = time_it(fn)
+            finally:
+                lib.cdll.dd4ml_debug_kspace(1)
+                ds.state.copy_(state_copy)
         byt = algorithmic_bytes(name, n, kk)
         out[name] = {"n": n, "k": kk, "ms": ms, "bytes": byt, "achieved": byt / ms / 1e6,
-                     "frac": byt / ms / 1e6 / peak_gbs}
+                     "frac": byt / ms / 1e6 / peak_gbs, "ms_entry_with_kspace_kernel": ms_entry,
+                     "frac_entry_with_kspace_kernel": byt / ms_entry / 1e6 / peak_gbs,
+                     "kspace_kernel_us": 1e3 * (ms_entry - ms)}
     sel = out.get(kernel) or out["dd4ml_lssr1_begin"]
     # DRAM traffic of the same kernel at the same (n, k) from the committed `ncu --set full` capture
     traffic = None
@@ -324,7 +344,11 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
     roof = {"bound": "hbm", "achieved": sel["achieved"], "peak": peak_gbs, "unit": "GB/s",
             "frac": sel["frac"], "traffic": traffic, "kernel": kernel if kernel in out else "dd4ml_lssr1_begin",
             "workload": f"fp32 n=2^26 k={sel['k']} (inputs >> L2)", "peak_source": peak_src,
-            "bytes_per_launch": sel["bytes"], "ms_per_launch": sel["ms"]}
+            "bytes_per_launch": sel["bytes"], "ms_per_launch": sel["ms"],
+            "what": "the streaming reduction kernel of the entry point, timed alone with CUDA events",
+            "entry_point_with_kspace_kernel": {"ms": sel["ms_entry_with_kspace_kernel"],
+                                               "frac": sel["frac_entry_with_kspace_kernel"],
+                                               "kspace_kernel_us": sel["kspace_kernel_us"]}}
     return roof, out
 
 

@@ -73,6 +73,7 @@ _SIGS = {
     "dd4ml_apts_foc": ([c_void_p] * 7 + [c_int, c_double, c_int64, c_int, c_int, c_void_p], c_int),
     "dd4ml_apts_pack": ([c_void_p] * 5 + [c_int, c_double, c_double, c_int64, c_int, c_int, c_void_p], c_int),
     "dd4ml_apts_trial": ([c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_int64, c_int, c_int, c_void_p], c_int),
+    "dd4ml_debug_kspace": ([c_int], c_int),
     "dd4ml_apts_combine": ([c_void_p, c_void_p, ctypes.POINTER(c_void_p), c_int, c_double, c_void_p, c_int64, c_int, c_int, c_void_p], c_int),
     "dd4ml_tradam_moments": ([c_void_p] * 5 + [c_double] * 6 + [c_int, c_int64, c_int, c_void_p], c_int),
     "dd4ml_tradam_apply": ([c_void_p] * 6 + [c_double] * 3 + [c_int64, c_int, c_int, c_void_p], c_int),
@@ -140,7 +141,7 @@ class Lib:
 # kernels launched per entry point
 # (the reduction kernel + the one-warp k-space kernel for the entry points that solve in k-space)
 _LAUNCHES = {"state_init": 2, "lsr1_B": 3, "tr_propose": 2, "lssr1_begin": 2, "tr_decide": 2, "lsr1_update": 2,
-             "version": 0, "error_string": 0}
+             "version": 0, "error_string": 0, "debug_kspace": 0}
 
 _LIB: Lib | None = None
 

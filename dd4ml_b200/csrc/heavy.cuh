@@ -38,6 +38,23 @@ struct PairRegs {
     }
 };
 
+// KMAX = 10 variants (the reference's default memory length): 20+ pair streams make the consumers of the
+// TMA ring latency bound on the LDS -> F2F.F64.F32 (quarter-rate XU pipe) -> DFMA chain with 40-70 fp64
+// accumulators (ncu, round 1: XU 31-44 %, F2F 17 % of the stall samples).  For all-float32 operands the
+// products of one thread-tile (V consecutive elements) are therefore summed in float32 FFMA chains and
+// only the per-tile partial is converted and added to the fp64 accumulator: V x fewer conversions,
+// 4-cycle FFMA latency in the chain.  The partial's rounding (V products, ~1e-7 relative) is below the
+// reference's own float32 dot products; sums stay deterministic.
+template <class A, class B> struct BothF32 { static constexpr bool value = false; };
+template <> struct BothF32<float, float> { static constexpr bool value = true; };
+template <int V>
+__device__ __forceinline__ float dot32(const float (&a)[V], const float (&b)[V]) {
+    float s = a[0] * b[0];
+#pragma unroll
+    for (int e = 1; e < V; ++e) s = fmaf(a[e], b[e], s);
+    return s;
+}
+
 #define DD4ML_KCAP_SWITCH(kcap, CALLK) \
     if ((kcap) <= 4) { CALLK(4) } else if ((kcap) <= 6) { CALLK(6) } else { CALLK(DD4ML_MAXM) }
 

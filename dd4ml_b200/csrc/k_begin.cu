@@ -78,22 +78,40 @@ struct LssrBeginOp {
                 acc[6] += yv[e] * gv[e];
             }
         }
+        if constexpr (KMAX > 6 && BothF32<HT, VT>::value && BothF32<WT, WT>::value && V > 1) {
+            float sf[V], yf[V];
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j)
-            if (sl.live(j)) {
+            for (int e = 0; e < V; ++e) { sf[e] = pair ? (float)sv[e] : 0.f; yf[e] = pair ? (float)yv[e] : 0.f; }   // exact: sv, yv are float32 values
 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
-                    acc[7 + j] += a * gv[e];
-                    acc[7 + KMAX + j] += b * gv[e];
+            for (int j = 0; j < KMAX; ++j)
+                if (sl.live(j)) {
+                    acc[7 + j] += (double)dot32<V>(pr.s[j].x, gr.x);
+                    acc[7 + KMAX + j] += (double)dot32<V>(pr.y[j].x, gr.x);
                     if (pair) {
-                        acc[7 + 2 * KMAX + j] += a * sv[e];
-                        acc[7 + 3 * KMAX + j] += b * sv[e];
-                        acc[7 + 4 * KMAX + j] += a * yv[e];
-                        acc[7 + 5 * KMAX + j] += b * yv[e];
+                        acc[7 + 2 * KMAX + j] += (double)dot32<V>(pr.s[j].x, sf);
+                        acc[7 + 3 * KMAX + j] += (double)dot32<V>(pr.y[j].x, sf);
+                        acc[7 + 4 * KMAX + j] += (double)dot32<V>(pr.s[j].x, yf);
+                        acc[7 + 5 * KMAX + j] += (double)dot32<V>(pr.y[j].x, yf);
                     }
                 }
-            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j)
+                if (sl.live(j)) {
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
+                        acc[7 + j] += a * gv[e];
+                        acc[7 + KMAX + j] += b * gv[e];
+                        if (pair) {
+                            acc[7 + 2 * KMAX + j] += a * sv[e];
+                            acc[7 + 3 * KMAX + j] += b * sv[e];
+                            acc[7 + 4 * KMAX + j] += a * yv[e];
+                            acc[7 + 5 * KMAX + j] += b * yv[e];
+                        }
+                    }
+                }
+        }
         if (pair) {
             st_v<V, HT>(S + (int64_t)spare * ld, i, sv);
             st_v<V, HT>(Y + (int64_t)spare * ld, i, yv);

@@ -94,18 +94,32 @@ struct DecideOp {
                 acc[1] += sv[e] * yv[e];
                 acc[2] += yv[e] * yv[e];
             }
+            if constexpr (KMAX > 6 && BothF32<HT, VT>::value && V > 1) {
+                float sf[V], yf[V];
 #pragma unroll
-            for (int j = 0; j < KMAX; ++j)
-                if (sl.live(j)) {
+                for (int e = 0; e < V; ++e) { sf[e] = (float)sv[e]; yf[e] = (float)yv[e]; }   // exact: float32 values
 #pragma unroll
-                    for (int e = 0; e < V; ++e) {
-                        const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
-                        acc[5 + j] += a * sv[e];
-                        acc[5 + KMAX + j] += b * sv[e];
-                        acc[5 + 2 * KMAX + j] += a * yv[e];
-                        acc[5 + 3 * KMAX + j] += b * yv[e];
+                for (int j = 0; j < KMAX; ++j)
+                    if (sl.live(j)) {
+                        acc[5 + j] += (double)dot32<V>(pr.s[j].x, sf);
+                        acc[5 + KMAX + j] += (double)dot32<V>(pr.y[j].x, sf);
+                        acc[5 + 2 * KMAX + j] += (double)dot32<V>(pr.s[j].x, yf);
+                        acc[5 + 3 * KMAX + j] += (double)dot32<V>(pr.y[j].x, yf);
                     }
-                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < KMAX; ++j)
+                    if (sl.live(j)) {
+#pragma unroll
+                        for (int e = 0; e < V; ++e) {
+                            const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
+                            acc[5 + j] += a * sv[e];
+                            acc[5 + KMAX + j] += b * sv[e];
+                            acc[5 + 2 * KMAX + j] += a * yv[e];
+                            acc[5 + 3 * KMAX + j] += b * yv[e];
+                        }
+                    }
+            }
             st_v<V, HT>(S + (int64_t)spare * ld, i, sv);
             st_v<V, HT>(Y + (int64_t)spare * ld, i, yv);
         }
@@ -175,18 +189,32 @@ struct UpdateOp {
             acc[1] += sv[e] * yv[e];
             acc[2] += yv[e] * yv[e];
         }
+        if constexpr (KMAX > 6 && BothF32<HT, VT>::value && V > 1) {
+            float sf[V], yf[V];
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j)
-            if (sl.live(j)) {
+            for (int e = 0; e < V; ++e) { sf[e] = (float)sv[e]; yf[e] = (float)yv[e]; }       // exact: float32 values
 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
-                    acc[3 + j] += a * sv[e];
-                    acc[3 + KMAX + j] += b * sv[e];
-                    acc[3 + 2 * KMAX + j] += a * yv[e];
-                    acc[3 + 3 * KMAX + j] += b * yv[e];
+            for (int j = 0; j < KMAX; ++j)
+                if (sl.live(j)) {
+                    acc[3 + j] += (double)dot32<V>(pr.s[j].x, sf);
+                    acc[3 + KMAX + j] += (double)dot32<V>(pr.y[j].x, sf);
+                    acc[3 + 2 * KMAX + j] += (double)dot32<V>(pr.s[j].x, yf);
+                    acc[3 + 3 * KMAX + j] += (double)dot32<V>(pr.y[j].x, yf);
                 }
-            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j)
+                if (sl.live(j)) {
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const double a = (double)pr.s[j].x[e], b = (double)pr.y[j].x[e];
+                        acc[3 + j] += a * sv[e];
+                        acc[3 + KMAX + j] += b * sv[e];
+                        acc[3 + 2 * KMAX + j] += a * yv[e];
+                        acc[3 + 3 * KMAX + j] += b * yv[e];
+                    }
+                }
+        }
         st_v<V, HT>(S + (int64_t)spare * ld, i, sv);
         st_v<V, HT>(Y + (int64_t)spare * ld, i, yv);
     }

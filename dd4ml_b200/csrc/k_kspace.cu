@@ -99,7 +99,18 @@ __global__ void __launch_bounds__(32) kspace_kernel(dd4ml_state* gst, KTask t) {
 
 }  // namespace
 
+static bool g_kspace_enabled = true;
+// Measurement hook (bench.py / tools): with the k-space kernel switched off an entry point launches only its
+// streaming reduction kernel, so that kernel can be timed alone with CUDA events (its results are then NOT
+// post-processed: never switch it off outside a micro-benchmark).
+extern "C" int dd4ml_debug_kspace(int on) {
+    const int was = g_kspace_enabled ? 1 : 0;
+    g_kspace_enabled = on != 0;
+    return was;
+}
+
 int dd4ml_ks_launch(double* state, const KTask& task, cudaStream_t stream) {
+    if (!g_kspace_enabled) return 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(1);
     cfg.blockDim = dim3(32);

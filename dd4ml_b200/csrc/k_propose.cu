@@ -38,15 +38,24 @@ struct ProposeOp {
             acc[0] += gv[e] * gv[e];
             acc[1] = fmax(acc[1], fabs(gv[e]));
         }
+        if constexpr (KMAX > 6 && BothF32<HT, VT>::value && V > 1) {
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j)
-            if (sl.live(j)) {
-#pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    acc[2 + j] += (double)pr.s[j].x[e] * gv[e];
-                    acc[2 + KMAX + j] += (double)pr.y[j].x[e] * gv[e];
+            for (int j = 0; j < KMAX; ++j)
+                if (sl.live(j)) {
+                    acc[2 + j] += (double)dot32<V>(pr.s[j].x, gr.x);
+                    acc[2 + KMAX + j] += (double)dot32<V>(pr.y[j].x, gr.x);
                 }
-            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j)
+                if (sl.live(j)) {
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        acc[2 + j] += (double)pr.s[j].x[e] * gv[e];
+                        acc[2 + KMAX + j] += (double)pr.y[j].x[e] * gv[e];
+                    }
+                }
+        }
     }
     __device__ void finalize(const double* s, dd4ml_state* t) {   // the solve itself: k-space kernel (KT_SOLVE / KT_B / KT_SMW)
         t->gg[0] = s[0];

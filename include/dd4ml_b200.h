@@ -184,6 +184,11 @@ int dd4ml_lsr1_update(double* state, double* ws, const void* s, const void* y, v
 int dd4ml_lsr1_B(double* state, double* ws, const void* v, const void* S, const void* Y, void* out,
                  int64_t n, int64_t ld, int vt, int ht, int kcap, void* stream);
 
+/* ---- measurement hook: switch the one-warp k-space kernel that follows tr_propose / lssr1_begin /
+ * tr_decide / lsr1_update off (0) or on (1) so that the streaming reduction kernel can be timed alone;
+ * returns the previous setting.  Results are not post-processed while it is off. */
+int dd4ml_debug_kspace(int on);
+
 #ifdef __cplusplus
 }
 #endif

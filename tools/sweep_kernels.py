@@ -8,4 +8,6 @@ n = int(os.environ.get("SWEEP_N", 1 << 26))
 k = int(os.environ.get("SWEEP_K", 3))
 roof, out = large_n_roofline(torch.device("cuda", 0), "dd4ml_lssr1_begin", peak, "measured", n=n, k=k, iters=int(os.environ.get("SWEEP_ITERS", 10)))
 for name, v in out.items():
-    print(f"{name:22s} n={v['n']} k={v['k']} {v['ms']:.4f} ms  {v['achieved']:.0f} GB/s  frac {v['frac']:.3f}")
+    print(f"{name:22s} n={v['n']} k={v['k']} {v['ms']:.4f} ms  {v['achieved']:.0f} GB/s  frac {v['frac']:.3f}   "
+          f"(entry point incl. k-space kernel: {v['ms_entry_with_kspace_kernel']:.4f} ms, frac "
+          f"{v['frac_entry_with_kspace_kernel']:.3f})")
