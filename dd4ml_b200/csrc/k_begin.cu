@@ -183,5 +183,5 @@ extern "C" int dd4ml_lssr1_begin(double* state, double* ws, const void* w, const
     t.kind = KT_BEGIN;
     t.ht = ht; t.vt = vt; t.lt = lt;
     t.has_prev = has_prev;
-    return dd4ml_ks_launch(state, t, s);
+    return dd4ml_ks_launch(state, t, s, kcap);
 }

@@ -288,7 +288,7 @@ int dd4ml_tr_decide(double* state, double* ws, const void* loss, const void* tri
     t.kind = KT_DECIDE;
     t.ht = ht; t.vt = vt; t.lt = lt;
     t.mem = S ? 1 : 0;
-    return dd4ml_ks_launch(state, t, s);
+    return dd4ml_ks_launch(state, t, s, kcap);
 }
 
 int dd4ml_lsr1_update(double* state, double* ws, const void* s_in, const void* y_in, void* S, void* Y,
@@ -304,7 +304,7 @@ int dd4ml_lsr1_update(double* state, double* ws, const void* s_in, const void* y
     KTask t{};
     t.kind = KT_UPDATE;
     t.ht = ht; t.vt = vt;
-    return dd4ml_ks_launch(state, t, s);
+    return dd4ml_ks_launch(state, t, s, kcap);
 }
 
 }  // extern "C"

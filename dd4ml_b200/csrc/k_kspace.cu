@@ -1,4 +1,4 @@
-// The one-warp k-space kernel: see kspace_task.h and kspace.h.
+// The one-CTA k-space kernel (1 warp for memories of up to 5 pairs, 4 warps above): see kspace_task.h and kspace.h.
 #include <stdint.h>
 
 #include "kspace.h"
@@ -17,7 +17,7 @@ __device__ __noinline__ void finish_any(dd4ml_state* st, int lt, bool accept, do
     ks::tr_finish(st, accept, rho, lt == 0, scr);
 }
 
-__global__ void __launch_bounds__(32) kspace_kernel(dd4ml_state* gst, KTask t) {
+__global__ void __launch_bounds__(128) kspace_kernel(dd4ml_state* gst, KTask t) {
     __shared__ dd4ml_state st;
     __shared__ ks::Scratch scr;
     constexpr int NST = (int)(sizeof(dd4ml_state) / sizeof(double));
@@ -26,8 +26,8 @@ __global__ void __launch_bounds__(32) kspace_kernel(dd4ml_state* gst, KTask t) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     double* g = reinterpret_cast<double*>(gst);
     double* s = reinterpret_cast<double*>(&st);
-    for (int i = threadIdx.x; i < NST; i += 32) s[i] = __ldcg(g + i);
-    __syncwarp();
+    for (int i = threadIdx.x; i < NST; i += blockDim.x) s[i] = __ldcg(g + i);
+    __syncthreads();
     int mode = 0;
     bool do_solve = false, restore_ninf = false;
     double ninf_saved = 0.0;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(32) kspace_kernel(dd4ml_state* gst, KTask t) {
             const bool pair = t.has_prev && st.second_order[0] != 0.0;
             const int spare = (int)st.spare[0];
             const double ninf = st.norm_inf[0];
-            __syncwarp();
+            __syncthreads();
             if (pair && gn > tol && sqrt(st.c_ss[0]) > tol && sqrt(st.c_yy[0]) > tol) {  // lssr1_tr.py:521
                 if (threadIdx.x == 0) st.pair_tried[0] = 1.0;
                 if (ks::lsr1_try_update(&st, &scr)) {
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(32) kspace_kernel(dd4ml_state* gst, KTask t) {
                 }
             }
             if (threadIdx.x == 0) st.norm_inf[0] = 0.0;      // LSSR1_TR forces the 2-norm (lssr1_tr.py:94)
-            __syncwarp();
+            __syncthreads();
             mode = 1;
             do_solve = true;
             restore_ninf = true;
@@ -71,16 +71,16 @@ __global__ void __launch_bounds__(32) kspace_kernel(dd4ml_state* gst, KTask t) {
                 ? ks::tr_accept<float>(st.loss[0], st.trial_loss[0], st.pred[0], st.tol[0], st.nu_dec[0], &rho)
                 : ks::tr_accept<double>(st.loss[0], st.trial_loss[0], st.pred[0], st.tol[0], st.nu_dec[0], &rho);
             const double so = st.second_order[0];
-            __syncwarp();
+            __syncthreads();
             if (!t.mem && threadIdx.x == 0) st.second_order[0] = 0.0;
-            __syncwarp();
+            __syncthreads();
             finish_any(&st, t.lt, accept, rho, &scr);
             if (threadIdx.x == 0) { st.second_order[0] = so; st.solve_valid[0] = 0.0; }
             break;
         }
         case KT_UPDATE:
             if (threadIdx.x == 0) { st.err[0] = 0.0; st.pair_tried[0] = 1.0; }
-            __syncwarp();
+            __syncthreads();
             ks::lsr1_try_update(&st, &scr);
             if (threadIdx.x == 0) st.solve_valid[0] = 0.0;
             break;
@@ -91,10 +91,10 @@ __global__ void __launch_bounds__(32) kspace_kernel(dd4ml_state* gst, KTask t) {
         solve_any(&st, mode, t.ht, t.vt, &scr);
         if (restore_ninf && threadIdx.x == 0) st.norm_inf[0] = ninf_saved;
     }
-    __syncwarp();
+    __syncthreads();
     if (threadIdx.x == 0 && st.err[0] != 0.0) st.err_seen[0] = st.err[0];
-    __syncwarp();
-    for (int i = threadIdx.x; i < NST; i += 32) g[i] = s[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < NST; i += blockDim.x) g[i] = s[i];
 }
 
 }  // namespace
@@ -109,11 +109,11 @@ extern "C" int dd4ml_debug_kspace(int on) {
     return was;
 }
 
-int dd4ml_ks_launch(double* state, const KTask& task, cudaStream_t stream) {
+int dd4ml_ks_launch(double* state, const KTask& task, cudaStream_t stream, int kcap) {
     if (!g_kspace_enabled) return 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(1);
-    cfg.blockDim = dim3(32);
+    cfg.blockDim = dim3(kcap > 5 ? 128 : 32);   // parallel regions are k x k .. k x 2k elements wide
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];

@@ -98,5 +98,5 @@ extern "C" int dd4ml_tr_propose(double* state, double* ws, const void* g, const 
     t.kind = mode == 2 ? KT_B : (mode == 3 ? KT_SMW : KT_SOLVE);
     t.mode = mode;
     t.ht = ht; t.vt = vt;
-    return dd4ml_ks_launch(state, t, s);
+    return dd4ml_ks_launch(state, t, s, kcap);
 }

@@ -2,22 +2,30 @@
 // reductions over the n-vectors and the streaming output pass.
 //
 // All inputs are O(k^2) numbers (Gram blocks of the L-SR1 pairs, Psi^T g, g^T g) held in the device
-// state block.  The routines run in the ONE-WARP k-space kernel (k_kspace.cu) that follows every
-// reduction kernel ("small m x m inner solve kept in one CTA"): the k x k matrices live in shared
-// memory and every O(k^2)/O(k^3) step is a *parallel region* over matrix elements / rows / columns /
-// Jacobi rotation pairs, so the dependent chain is O(k) steps per factorisation instead of O(k^3)
-// scalar operations in one thread.  The code is loop based and compact on purpose: it is executed
-// once per launch right after the closure's kernels have evicted the instruction cache, so its
-// footprint, not its flop count, sets its latency.
+// state block.  The routines run in the ONE-CTA k-space kernel (k_kspace.cu: one warp for memories of
+// up to 5 pairs, four warps above) that follows every reduction kernel ("small m x m inner solve kept in
+// one CTA").  The kernel is pure latency: it runs once per launch, right after the closure's kernels
+// have evicted the instruction cache, on O(k^3) flops.  What sets its duration is therefore
+//   (1) the number of DISTINCT instructions (cold fetch: ~7 cycles each) -- one shared copy of every
+//       building block (Gauss-Jordan, small dot product, division, square root), no unrolled variants;
+//   (2) the length of the dependent chain -- every O(k^2)/O(k^3) step is a *parallel region* over
+//       matrix elements, and the algorithms are chosen for few, wide regions:
+//         * Cholesky of the AUGMENTED block [Psi^T Psi | Psi^T g]: the extra column comes out as
+//           R^-T Psi^T g, so that a = U^T (R^-T Psi^T g) needs no triangular solve per eigenvector;
+//         * M^-1 by Gauss-Jordan with partial pivoting between two buffers (ONE region per pivot: no
+//           row-swap / multiplier / update phases), after which every solve is a matrix-vector product;
+//         * two-sided Jacobi with the round-robin ordering, rotations of a round applied to A and V in
+//           ONE region between two buffers (A' = J^T A J element-wise from 4 old entries).
 //
 // Execution model (also what lets tests/hostshim compile this file for the CPU):
 //   KS_PAR(i, n) { body }  KS_SYNC();      a parallel region: iterations are independent -- an iteration
 //                                          never reads what another iteration of the same region writes
-//   everything else                        uniform code, executed redundantly by all lanes; shared state is
-//                                          written by the master lane only (KS_MASTER) and never read back
-//                                          before the next KS_SYNC()
-// On the device KS_PAR strides the lanes of the warp and KS_SYNC is __syncwarp(); on the host KS_PAR is a
-// plain loop and KS_SYNC a no-op, which is the same program by the independence rule.
+//   everything else                        uniform code, executed redundantly by all threads; shared state
+//                                          is written by the master thread only (KS_MASTER), is never read
+//                                          back before the next KS_SYNC(), and nothing that uniform code
+//                                          has read is overwritten before the next KS_SYNC()
+// On the device KS_PAR strides the threads of the CTA and KS_SYNC is a CTA barrier; on the host KS_PAR is
+// a plain loop and KS_SYNC a no-op, which is the same program by the independence rule.
 //
 // Reference behaviour restated here (cruzas/DD4ML):
 //   LSR1.precompute / B / update_memory      optimizers/lsr1.py:53-198
@@ -25,7 +33,7 @@
 //   solve_tr_first_order / second_order      utility/optimizer_utils.py:197-307
 //   TR.step ratio test and radius update     optimizers/tr.py:186-221
 //   LSSR1_TR clip-to-radius / descent flip   optimizers/lssr1_tr.py:563-587
-// Linear algebra (Cholesky, LU, symmetric eigen-decomposition) runs in double; the quantities the
+// Linear algebra (Cholesky, Gauss-Jordan, symmetric eigen-decomposition) runs in double; the quantities the
 // reference thresholds or iterates on in its working dtype (Lambda, a_j, the Newton iteration, rho) are
 // rounded to that dtype T first.
 #pragma once
@@ -35,7 +43,7 @@
 
 #ifdef __CUDACC__
 #define KS_FN __host__ __device__
-#define KS_BIG __host__ __device__ __noinline__    // one copy of every large routine: code size is latency here
+#define KS_BIG __host__ __device__ __noinline__    // one copy of every shared routine: code size is latency here
 #define KS_LOOP _Pragma("unroll 1")
 #else
 #define KS_FN
@@ -44,39 +52,89 @@
 #endif
 #if defined(__CUDA_ARCH__)
 #define KS_CLOCK() ((double)clock64())
-#define KS_RSQRT(x) rsqrt(x)
 #define KS_TID ((int)threadIdx.x)
 #define KS_NT ((int)blockDim.x)
-#define KS_SYNC() __syncwarp()
+#define KS_SYNC() __syncthreads()
 #else
 #define KS_CLOCK() 0.0
-#define KS_RSQRT(x) (1.0 / sqrt(x))
 #define KS_TID 0
 #define KS_NT 1
 #define KS_SYNC() ((void)0)
 #endif
 #define KS_PAR(i, n) KS_LOOP for (int i = KS_TID; i < (n); i += KS_NT)
 #define KS_MASTER if (KS_TID == 0)
-// 2-D region over a k x k block: slots e = i*M + j with the constant leading dimension M (division by a
-// constant, no runtime integer division), entries j >= k idle.  Usage: KS_PAR2(i, j, k) { ... } KS_END2
-#define KS_PAR2(i, j, k) KS_LOOP for (int e_ = KS_TID; e_ < (k) * M; e_ += KS_NT) { const int i = e_ / M, j = e_ - i * M; if (j < (k))
-#define KS_END2 }
-#ifdef __CUDACC__
-#define KS_UNROLL _Pragma("unroll")
-#else
-#define KS_UNROLL
-#endif
+// 2-D region over rows x cols elements, every slot live: KS_PAR2(i, j, rows, cols) { ... } KS_END2
+#define KS_PAR2(i, j, rows, cols) { const ks::Div dv_(cols); const int ne_ = (rows) * (cols);                 \
+    KS_LOOP for (int e_ = KS_TID; e_ < ne_; e_ += KS_NT) { const int i = dv_.quot(e_), j = e_ - i * (cols);
+#define KS_END2 } }
 
 namespace ks {
 
 constexpr int M = DD4ML_MAXM;
 constexpr int MS = DD4ML_MAXS;
+constexpr int LD = M + 1;         // leading dimension of the k x k blocks (odd; column k can hold one more vector)
+constexpr int LW = 2 * M + 1;     // leading dimension of the Gauss-Jordan blocks [A | B]
 constexpr double OBS_TOL = 1e-6;  // obs.py:29
+
+// e / c for 0 <= e < 4096, 1 <= c <= 32 without an integer division: (e + 1/2) / c is at least 1/(2c)
+// away from an integer, far more than the float32 rounding error of the product
+struct Div {
+#if defined(__CUDA_ARCH__)
+    float inv;
+    __device__ explicit Div(int c) : inv(__fdividef(1.0f, (float)c)) {}
+    __device__ int quot(int e) const { return __float2int_rz(((float)e + 0.5f) * inv); }
+#else
+    int c;
+    explicit Div(int c_) : c(c_) {}
+    int quot(int e) const { return e / c; }
+#endif
+};
 
 KS_FN inline bool finite(double x) { return x == x && fabs(x) <= 1.79769313486231570e308; }
 // IEEE double division / square root expand to ~30 instructions each: one out-of-line copy
 KS_BIG inline double ddiv(double a, double b) { return a / b; }
 KS_BIG inline double dsqrt(double x) { return sqrt(x); }
+KS_BIG inline double drsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+// 2^-floor(log2 |x|) for a normal x (1 for 0 / subnormal / non-finite x): exact exponent normalisation
+KS_FN inline double pow2_inv(double x) {
+#if defined(__CUDA_ARCH__)
+    const int e = (__double2hiint(x) >> 20) & 0x7ff;
+    return (e == 0 || e >= 0x7fe) ? 1.0 : __hiloint2double((2046 - e) << 20, 0);
+#else
+    if (!(fabs(x) >= 2.2250738585072014e-308) || !(fabs(x) <= 8.9e307)) return 1.0;
+    int ex;
+    (void)frexp(x, &ex);
+    return ldexp(1.0, 1 - ex);
+#endif
+}
+// |tan| of the Jacobi rotation from the exponent-normalised (aqq - app, 2 apq): any value within ~1e-6
+// relative of |a| / (|d| + sqrt(d^2 + a^2)) will do (see jacobi_core), so the device uses the approximate
+// float32 reciprocal / square root units
+KS_FN inline float rot_tan(float df, float af) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(fabsf(af), fabsf(df) + __fsqrt_rn(fmaf(df, df, af * af)));
+#else
+    return fabsf(af) / (fabsf(df) + sqrtf(df * df + af * af));
+#endif
+}
+// 1 / sqrt(1 + t^2) to double precision (|t| <= 1): float32 seed + two Newton steps, in line
+KS_FN inline double rot_cos(double t) {
+    const double h = t * t + 1.0;
+#if defined(__CUDA_ARCH__)
+    double c = (double)rsqrtf((float)h);
+    c = c * (1.5 - 0.5 * h * c * c);
+    c = c * (1.5 - 0.5 * h * c * c);
+    return c;
+#else
+    return 1.0 / sqrt(h);
+#endif
+}
 // Round to the reference's working dtype (float32 or float64).  A float32 operation on float32
 // operands equals the float64 operation rounded to float32 (53 >= 2*24 + 2 bits: no double-rounding
 // error for + - * / sqrt), so `rT(a op b, f32)` IS the reference's float32 arithmetic.
@@ -84,18 +142,23 @@ KS_FN inline double rT(double x, bool f32) { return f32 ? (double)(float)x : x; 
 KS_FN inline float ks_sqrt(float x) { return sqrtf(x); }
 KS_FN inline double ks_sqrt(double x) { return sqrt(x); }
 
-// Work arrays of the k-space routines: shared memory of the k-space kernel (row-major, leading
-// dimension M).
+// Work arrays of the k-space routines: shared memory of the k-space kernel.  k x k blocks are row-major
+// with leading dimension LD, the Gauss-Jordan blocks with LW.
 struct Scratch {
-    double Minv[M * M];  // diag(S^T Y) + L + L^T - gamma S^T S + tol*||.||_F I   (lsr1.py:168-179)
-    double G[M * M];     // Psi^T Psi
-    double R[M * M], LU[M * M], MR[M * M], RMR[M * M], U[M * M], V[M * M], RinvU[M * M], W[M * M];
-    double D[M], Dw[M], b[M], x[M], z[M], wv[M], Gw[M], bs[M], by[M], ad[M + 1];
+    double Minv[M * LD];  // diag(S^T Y) + L + L^T - gamma S^T S + tol*||.||_F I   (lsr1.py:168-179)
+    double G[M * LD];     // Psi^T Psi
+    double Mi[M * LD];    // Minv^{-1}
+    double R[M * LD];     // Cholesky factor of G (upper); column k: R^-T Psi^T g
+    double T[M * LD];     // Minv^{-1} R^T, then R Minv^{-1} R^T
+    double J0[M * LD], J1[M * LD], V0[M * LD], V1[M * LD];   // Jacobi: matrix and eigenvectors, two buffers each
+    double X0[M * LW], X1[M * LW];                           // Gauss-Jordan: two buffers
+    double vec[6 * M];    // b = Psi^T g, x = Minv\b, wv, G wv, z = Minv\(G wv), spare
+    double Rd[M], rowa[M], rowb[M], ad[M + 1], dot6[6];
+    double pacc[2 * M];   // per rotation slot: off-diagonal mass annihilated in this sweep (two sweeps alternate)
+    double rc[M], rt[M];  // Jacobi rotations of one round, per INDEX: new col j = rc[j] col j + rt[j] col mate[j]
+    int mate[M];
     double Ld[M + 1], Ad[M + 1];   // Lambda, a in the working dtype (T = double)
     float Lf[M + 1], Af[M + 1];    //                                 (T = float)
-    double rc[M], rs[M];           // Jacobi rotations of one round
-    int rp[M], rq[M], rank[M];
-    int piv[M], pw[M];
 };
 template <class T> struct LamA;
 template <> struct LamA<float> {
@@ -107,125 +170,130 @@ template <> struct LamA<double> {
     KS_FN static double* a(Scratch* ws) { return ws->Ad; }
 };
 
-// sum_{i<k} a[i*sa] * b[i*sb].  ONE out-of-line copy with a runtime loop: the k-space kernel is bound by
-// instruction issue / fetch of a single warp (ncu: ~5 cycles per instruction, half of the stall samples
-// `no_instruction`), so the dynamic instruction count and the code footprint are what matter -- a
-// predicated unroll to M terms executes M/k times the instructions and was measured slower.
+// sum_{i<k} a[i*sa] * b[i*sb] (per thread).  ONE out-of-line copy.  All operands are fetched before the
+// first multiply (the shared-memory latency is paid once, not once per term) in fixed-size batches of 4:
+// terms beyond k are predicated off.
 KS_BIG inline double dots(const double* a, int sa, const double* b, int sb, int k) {
     double s = 0.0;
+#if defined(__CUDA_ARCH__)
     KS_LOOP
+    for (int i0 = 0; i0 < k; i0 += 4, a += 4 * sa, b += 4 * sb) {
+        double x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool on = i0 + u < k;
+            x[u] = on ? a[u * sa] : 0.0;
+            y[u] = on ? b[u * sb] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) s += x[u] * y[u];
+    }
+#else
     for (int i = 0; i < k; ++i) s += a[i * sa] * b[i * sb];
+#endif
     return s;
 }
 KS_FN inline double dotk(const double* a, const double* b, int k) { return dots(a, 1, b, 1, k); }
 
-// ---- dense helpers on row-major k x k blocks with leading dimension M (collective) -----------
-// R upper triangular with R^T R = G (torch.linalg.cholesky(upper=True)).  One column per step:
-// the pivot is uniform scalar work, the row to its right a parallel region.
-KS_BIG inline bool chol_upper(const double* G, int k, double* R) {
-    KS_PAR(e, k * M) R[e] = 0.0;
+// C[i*ldc + j] = sum_{l<nl} A[i*sai + l*sal] * B[l*sbl + j*sbj], i < ni, j < nj.  Collective.
+KS_BIG inline void mm(double* C, int ldc, const double* A, int sai, int sal, const double* B, int sbl, int sbj,
+                      int ni, int nj, int nl) {
+    KS_PAR2(i, j, ni, nj) { C[i * ldc + j] = dots(A + i * sai, sal, B + j * sbj, sbl, nl); } KS_END2
     KS_SYNC();
-    KS_LOOP
-    for (int j = 0; j < k; ++j) {
-        const double s = G[j * M + j] - dots(R + j, M, R + j, M, j);
-        if (!(s > 0.0) || !finite(s)) return false;
-        const double d = dsqrt(s);
-        KS_PAR(c, k) {
-            if (c == j) R[j * M + j] = d;
-            else if (c > j) R[j * M + c] = ddiv(G[j * M + c] - dots(R + j, M, R + c, M, j), d);
-        }
-        KS_SYNC();
-    }
-    return true;
 }
 
-// In-place LU with partial pivoting (torch.linalg.solve = getrf/getrs): pivot search uniform; row
-// swap, multipliers and the rank-1 update of the trailing block are parallel regions.
-KS_BIG inline bool lu_factor(double* A, int k, int* piv) {
+// Gauss-Jordan elimination with partial pivoting (the pivot rule of torch.linalg.solve's getrf) of the
+// k x w block [A | B] in ws->X0 (w > k, leading dimension LW).  ONE region per pivot: element (i, j) of
+// the next block is formed from the current one -- row swap, normalisation of the pivot row and
+// elimination of column c from every other row at once -- in the other buffer.  Columns <= c are dead
+// (unit vectors) and skipped.  Returns the buffer whose columns k..w-1 hold A^{-1} B, nullptr when a pivot
+// is exactly zero or non-finite.  Collective.
+KS_BIG inline double* gauss_jordan(Scratch* ws, int k, int w) {
+    double* src = ws->X0;
+    double* dst = ws->X1;
     KS_LOOP
     for (int c = 0; c < k; ++c) {
         int p = c;
-        double best = fabs(A[c * M + c]);
+        double best = fabs(src[c * LW + c]);
         KS_LOOP
         for (int r = c + 1; r < k; ++r) {
-            const double v = fabs(A[r * M + c]);
+            const double v = fabs(src[r * LW + c]);
             if (v > best) { best = v; p = r; }
         }
-        if (best == 0.0 || !finite(best)) return false;
-        KS_SYNC();                      // every lane has read column c before rows move
-        KS_PAR(j, k) {
-            if (j == 0) piv[c] = p;
-            if (p != c) { const double t = A[c * M + j]; A[c * M + j] = A[p * M + j]; A[p * M + j] = t; }
+        if (best == 0.0 || !finite(best)) return nullptr;
+        const double inv = ddiv(1.0, src[p * LW + c]);
+        const int nc = w - c - 1;
+        KS_PAR2(i, jj, k, nc) {
+            const int j = c + 1 + jj;
+            const int ri = (i == c) ? p : ((i == p) ? c : i);      // row i after the swap c <-> p
+            const double pj = src[p * LW + j] * inv;              // normalised pivot row
+            dst[i * LW + j] = (i == c) ? pj : src[ri * LW + j] - src[ri * LW + c] * pj;
+        } KS_END2
+        KS_SYNC();
+        double* t = src; src = dst; dst = t;
+    }
+    return src;
+}
+
+// R upper triangular with R^T R = G (torch.linalg.cholesky(upper=True)), right-looking, on the block
+// [G | b] (b in column k): one region scales the pivot row, one updates the trailing block, so that
+// on exit R[:, k] = R^-T b.  Strictly lower part zero.  Collective.
+KS_BIG inline bool chol_aug(Scratch* ws, int k) {
+    double* R = ws->R;
+    const double* b = ws->vec;
+    KS_PAR2(i, j, k, k + 1) { R[i * LD + j] = (j == k) ? b[i] : ((j >= i) ? ws->G[i * LD + j] : 0.0); } KS_END2
+    KS_SYNC();
+    KS_LOOP
+    for (int j = 0; j < k; ++j) {
+        const double s = R[j * LD + j];
+        if (!(s > 0.0) || !finite(s)) return false;
+        const double inv = drsqrt(s);
+        const int w = k - j;               // columns j+1 .. k
+        KS_PAR(c, w + 1) {
+            if (c == w) ws->Rd[j] = s * inv;
+            else R[j * LD + j + 1 + c] *= inv;
         }
         KS_SYNC();
-        const double inv = ddiv(1.0, A[c * M + c]);
-        KS_PAR(r, k) { if (r > c) A[r * M + c] *= inv; }          // multipliers
-        KS_SYNC();
-        KS_PAR2(r, j, k) {              // trailing block
-            if (r > c && j > c) A[r * M + j] -= A[r * M + c] * A[c * M + j];
+        KS_PAR2(a, c, k - 1 - j, w) {      // rows j+1 .. k-1
+            const int i = j + 1 + a, cc = j + 1 + c;
+            if (cc >= i) R[i * LD + cc] -= R[j * LD + i] * R[j * LD + cc];
         } KS_END2
         KS_SYNC();
     }
+    KS_PAR(j, k) R[j * LD + j] = ws->Rd[j];
+    KS_SYNC();
     return true;
 }
 
-// v <- A^{-1} v from the factorisation (per lane, not collective); v has stride ldv
-KS_BIG inline void lu_solve_vec(const double* LU, const int* piv, int k, double* v, int ldv) {
-    KS_LOOP
-    for (int i = 0; i < k; ++i) {
-        const int p = piv[i];
-        if (p != i) { const double t = v[i * ldv]; v[i * ldv] = v[p * ldv]; v[p * ldv] = t; }
-    }
-    KS_LOOP
-    for (int r = 1; r < k; ++r) v[r * ldv] -= dots(LU + r * M, 1, v, ldv, r);
-    KS_LOOP
-    for (int r = k - 1; r >= 0; --r) {
-        const double s = v[r * ldv] - dots(LU + r * M + r + 1, 1, v + (r + 1) * ldv, ldv, k - r - 1);
-        v[r * ldv] = ddiv(s, LU[r * M + r]);
-    }
-}
-
-// X[:, c] <- A^{-1} X[:, c] for c < ncols (one right-hand side per lane).  Collective.
-KS_FN inline void lu_solve_cols(const double* LU, const int* piv, int k, double* X, int ldx, int ncols) {
-    KS_PAR(c, ncols) lu_solve_vec(LU, piv, k, X + c, ldx);
-    KS_SYNC();
-}
-
-// Jacobi eigen-decomposition of a symmetric k x k matrix with the round-robin (tournament) ordering:
-// the floor(k/2) rotations of a round touch disjoint index pairs and are applied together -- k-1 (k)
-// rounds per sweep instead of k(k-1)/2 dependent rotations.  On exit w ascending, U[:, j] the
-// eigenvector of w[j], each with its largest-|.| component positive (lowest index on ties): the
-// documented sign convention of this implementation.  A is destroyed.
+// Jacobi eigen-decomposition of the symmetric k x k matrix in ws->J0 (destroyed) with the round-robin
+// (tournament) ordering: the floor(k/2) rotations of a round touch disjoint index pairs and are applied
+// together -- k-1 (k) rounds per sweep instead of k(k-1)/2 dependent rotations.  A round is two regions:
+// the rotation angles (per index j: partner mate[j] and the coefficients of new col j = rc[j] col j +
+// rt[j] col mate[j]), then A' = J^T A J and V' = V J element by element into the other buffers.
+// The sweeps stop when the off-diagonal mass annihilated by a whole sweep is below 1e-20 of ||A||_F^2
+// (Jacobi converges quadratically: what is left after that sweep is far below 1e-13 ||A||_F).
+// On exit *Aout / *Vout point at the buffers with the diagonalised matrix / the eigenvectors (columns,
+// unsorted, unnormalised signs).  Returns the number of sweeps.  Collective.
 // The rotation angle is computed in float32 on exponent-normalised inputs (any angle keeps the
 // transformation orthogonal as long as c = 1/sqrt(1 + t^2) and s = t c are formed in double; a 1e-7
 // relative error of t only leaves 1e-7 of the pivot behind for the next sweep), which takes the
 // double-precision division and square root off the dependent chain of every round.
-KS_BIG inline int jacobi_eigh(double* A, int k, double* w, double* U, Scratch* ws) {
-    double* V = ws->V;
-    KS_PAR2(i, j, k) { V[i * M + j] = (i == j) ? 1.0 : 0.0; } KS_END2
+KS_BIG inline int jacobi_core(Scratch* ws, int k, double** Aout, double** Vout) {
+    double *A = ws->J0, *A2 = ws->J1, *V = ws->V0, *V2 = ws->V1;
+    KS_PAR2(i, j, k, k) { V[i * LD + j] = (i == j) ? 1.0 : 0.0; } KS_END2
+    KS_PAR(i, k) ws->rowa[i] = dots(A + i * LD, 1, A + i * LD, 1, k);
     KS_SYNC();
+    double fro = 0.0;
+    KS_LOOP
+    for (int i = 0; i < k; ++i) fro += ws->rowa[i];
+    const double thr = 1e-13 * fro;
     const int n = k + (k & 1);          // players of the tournament (one dummy when k is odd)
     const int half = n >> 1;
     int sweeps = 0;
     KS_LOOP
-    for (int sweep = 0; sweep < 64 && k > 1; ++sweep) {
-        KS_PAR(i, k) {                  // off-diagonal / diagonal mass, one row per lane
-            double o = 0.0;         // (summed directly: total - diagonal would cancel at the 1e-26 threshold)
-            KS_LOOP
-            for (int j = 0; j < k; ++j)
-                if (j != i) o += A[i * M + j] * A[i * M + j];
-            ws->rc[i] = o;
-            ws->rs[i] = A[i * M + i] * A[i * M + i];
-        }
-        KS_SYNC();
-        double off = 0.0, diag = 0.0;
-        KS_LOOP
-        for (int i = 0; i < k; ++i) { off += ws->rc[i]; diag += ws->rs[i]; }
-        KS_SYNC();                      // rc / rs are reused for the rotations
-        // off-diagonal mass (each entry counted twice) below 1e-26 of the diagonal mass: eigenvalues
-        // converged to ~1e-26 relative (Jacobi converges quadratically), eigenvectors to ~1e-13
-        if (0.5 * off <= 1e-26 * diag || off == 0.0) break;
-        ++sweeps;
+    for (int sweep = 0; sweep < 40 && k > 1; ++sweep) {
+        double* pacc = ws->pacc + (sweep & 1) * M;
+        KS_PAR(t, half) pacc[t] = 0.0;  // (slot t is only touched by its own thread until the sweep's last barrier)
         KS_LOOP
         for (int round = 0; round < n - 1; ++round) {
             KS_PAR(t, half) {           // rotation of pair t of this round
@@ -237,76 +305,72 @@ KS_BIG inline int jacobi_eigh(double* A, int k, double* w, double* U, Scratch* w
                 }
                 if (p > q) { const int u = p; p = q; q = u; }
                 double c = 1.0, s = 0.0;
+                int mp = p;
                 if (q < k) {
-                    const double apq = A[p * M + q];
+                    mp = q;
+                    const double apq = A[p * LD + q];
                     if (apq != 0.0) {
                         // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq)
-                        const double d = A[q * M + q] - A[p * M + p];
+                        const double d = A[q * LD + q] - A[p * LD + p];
                         const double a2 = 2.0 * apq;
-                        int ex;
-                        (void)frexp(fmax(fabs(d), fabs(a2)), &ex);
-                        const float df = (float)ldexp(d, -ex), af = (float)ldexp(a2, -ex);
-                        const float tf = fabsf(af) / (fabsf(df) + sqrtf(df * df + af * af));
+                        const double sc = pow2_inv(fmax(fabs(d), fabs(a2)));
+                        const float df = (float)(d * sc), af = (float)(a2 * sc);
+                        const float tf = rot_tan(df, af);
                         const double tt = ((d >= 0.0) == (a2 >= 0.0)) ? (double)tf : -(double)tf;
-                        c = KS_RSQRT(tt * tt + 1.0);
+                        c = rot_cos(tt);
                         s = tt * c;
+                        pacc[t] += apq * apq;
                     }
+                    ws->mate[q] = p; ws->rc[q] = c; ws->rt[q] = s;
                 }
-                ws->rp[t] = p; ws->rq[t] = q; ws->rc[t] = c; ws->rs[t] = s;
+                ws->mate[p] = mp; ws->rc[p] = c; ws->rt[p] = -s;      // (q >= k: p sits this round out)
             }
             KS_SYNC();
-            KS_PAR2(t, r, k) {          // A <- A J, V <- V J: entry pairs (r, p), (r, q) of every row r
-                if (t < half) {
-                    const int p = ws->rp[t], q = ws->rq[t];
-                    if (q < k) {
-                        const double c = ws->rc[t], s = ws->rs[t];
-                        const double arp = A[r * M + p], arq = A[r * M + q];
-                        const double vrp = V[r * M + p], vrq = V[r * M + q];
-                        A[r * M + p] = c * arp - s * arq;
-                        A[r * M + q] = s * arp + c * arq;
-                        V[r * M + p] = c * vrp - s * vrq;
-                        V[r * M + q] = s * vrp + c * vrq;
-                    }
-                }
+            KS_PAR2(i, j, k, k) {
+                const int mi = ws->mate[i], mj = ws->mate[j];
+                const double ci = ws->rc[i], ti = ws->rt[i], cj = ws->rc[j], tj = ws->rt[j];
+                const double u = cj * A[i * LD + j] + tj * A[i * LD + mj];       // (A J)[i][j]
+                const double v = cj * A[mi * LD + j] + tj * A[mi * LD + mj];     // (A J)[mate i][j]
+                A2[i * LD + j] = ci * u + ti * v;   // (the pivot keeps its ~1e-7 residue of the float32 angle: next sweep)
+                V2[i * LD + j] = cj * V[i * LD + j] + tj * V[i * LD + mj];
             } KS_END2
             KS_SYNC();
-            KS_PAR2(t, r, k) {          // A <- J^T A: entry pairs (p, r), (q, r) of every column r
-                if (t < half) {
-                    const int p = ws->rp[t], q = ws->rq[t];
-                    if (q < k) {
-                        const double c = ws->rc[t], s = ws->rs[t];
-                        const double apr = A[p * M + r], aqr = A[q * M + r];
-                        A[p * M + r] = c * apr - s * aqr;
-                        A[q * M + r] = s * apr + c * aqr;
-                    }
-                }
-            } KS_END2
-            KS_SYNC();
+            double* x = A; A = A2; A2 = x;
+            x = V; V = V2; V2 = x;
         }
-    }
-    // ascending order through ranks (stable on ties), then the sign convention per column
-    KS_PAR(j, k) {
-        const double wj = A[j * M + j];
-        int r = 0;
+        ++sweeps;
+        double tot = 0.0;
         KS_LOOP
-        for (int i = 0; i < k; ++i) {
-            const double wi = A[i * M + i];
-            r += (wi < wj || (wi == wj && i < j)) ? 1 : 0;
-        }
-        ws->rank[j] = r;
-        w[r] = wj;
+        for (int t = 0; t < half; ++t) tot += pacc[t];
+        if (!(tot > thr)) break;        // (also leaves on NaN)
     }
+    *Aout = A;
+    *Vout = V;
+    return sweeps;
+}
+
+// Stand-alone form (tests): w ascending, U[:, j] the eigenvector of w[j], each with its largest-|.|
+// component positive (lowest index on ties) -- the documented sign convention of this implementation
+// (DESIGN.md section 2.1).  Ain / U: row-major, leading dimension LD.
+KS_FN inline int jacobi_eigh(const double* Ain, int k, double* w, double* U, Scratch* ws) {
+    KS_PAR2(i, j, k, k) { ws->J0[i * LD + j] = Ain[i * LD + j]; } KS_END2
     KS_SYNC();
+    double *A, *V;
+    const int sweeps = jacobi_core(ws, k, &A, &V);
     KS_PAR(j, k) {
-        const int r = ws->rank[j];
-        int im = 0;
+        const double wj = A[j * LD + j];
+        int r = 0, im = 0;
         double best = -1.0;
         KS_LOOP
-        for (int i = 0; i < k; ++i)
-            if (fabs(V[i * M + j]) > best) { best = fabs(V[i * M + j]); im = i; }
-        const double sg = (V[im * M + j] < 0.0) ? -1.0 : 1.0;
+        for (int i = 0; i < k; ++i) {
+            const double wi = A[i * LD + i];
+            r += (wi < wj || (wi == wj && i < j)) ? 1 : 0;
+            if (fabs(V[i * LD + j]) > best) { best = fabs(V[i * LD + j]); im = i; }
+        }
+        const double sg = (V[im * LD + j] < 0.0) ? -1.0 : 1.0;
+        w[r] = wj;
         KS_LOOP
-        for (int i = 0; i < k; ++i) U[i * M + r] = sg * V[i * M + j];
+        for (int i = 0; i < k; ++i) U[i * LD + r] = sg * V[i * LD + j];
     }
     KS_SYNC();
     return sweeps;
@@ -399,48 +463,60 @@ KS_BIG inline T newton(T x0, const T* Lam, const T* a, int m, T delta, T tol, in
         ndeg += iters;
         return x;
     }
-    sec.fg(x, f, g, deg);
     iters = 0;
-    ndeg = deg ? 1 : 0;
+    ndeg = 0;
     KS_LOOP
-    while (fabs(f) > tol && iters < 200) {  // obs.py:217
-        x = x - f / g;
+    for (;;) {  // obs.py:217: evaluate; while |f| > tol and iters < 200: step, evaluate
         sec.fg(x, f, g, deg);
         ndeg += deg ? 1 : 0;
+        if (!(fabs(f) > tol) || iters >= 200) break;
+        x = x - f / g;
         ++iters;
     }
     return x;
 }
 
 // ---- logical (oldest..newest) views of the Gram blocks: Minv and G = Psi^T Psi (collective) ------
-KS_BIG inline void build_compact(const dd4ml_state* st, Scratch* ws) {
+// Returns false when a Gram entry is not finite.
+KS_BIG inline bool build_compact(const dd4ml_state* st, Scratch* ws) {
     const int k = (int)st->k[0];
     const double gam = st->gamma[0];
-    KS_PAR2(i, j, k) {
+    const bool mx = st->use_mx[0] != 0.0;
+    KS_PAR2(i, j, k, k) {
         const int pi = (int)st->order[i], pj = (int)st->order[j];
         const double sy_ij = st->SY[pi * MS + pj], sy_ji = st->SY[pj * MS + pi];
         const double ss = st->SS[pi * MS + pj], yy = st->YY[pi * MS + pj];
-        ws->Minv[i * M + j] = ((i >= j) ? sy_ij : sy_ji) - gam * ss;
-        ws->G[i * M + j] = yy - gam * (sy_ij + sy_ji) + gam * gam * ss;
-        if (st->use_mx[0] != 0.0) ws->Minv[i * M + j] = st->Mx[i * M + j];   // explicit Minv (already regularised)
+        ws->Minv[i * LD + j] = mx ? st->Mx[i * M + j]       // explicit Minv (already regularised)
+                                  : ((i >= j) ? sy_ij : sy_ji) - gam * ss;
+        ws->G[i * LD + j] = yy - gam * (sy_ij + sy_ji) + gam * gam * ss;
     } KS_END2
     KS_SYNC();
-    if (st->use_mx[0] != 0.0) return;
-    KS_PAR(i, k) ws->Dw[i] = dots(ws->Minv + i * M, 1, ws->Minv + i * M, 1, k);   // row sums of squares
+    KS_PAR(i, 2 * k) {                  // row sums of squares of Minv (i < k) and of G
+        const double* row = (i < k) ? ws->Minv + i * LD : ws->G + (i - k) * LD;
+        const double s = dots(row, 1, row, 1, k);
+        if (i < k) ws->rowa[i] = s; else ws->rowb[i - k] = s;
+    }
     KS_SYNC();
-    double fro = 0.0;
+    double fro = 0.0, frog = 0.0;
     KS_LOOP
-    for (int i = 0; i < k; ++i) fro += ws->Dw[i];
-    const double reg = st->tol[0] * dsqrt(fro);
-    KS_SYNC();                          // every lane has summed the unregularised matrix
-    KS_PAR(i, k) ws->Minv[i * M + i] += reg;
-    KS_SYNC();
+    for (int i = 0; i < k; ++i) { fro += ws->rowa[i]; frog += ws->rowb[i]; }
+    if (!mx) {
+        const double reg = st->tol[0] * dsqrt(fro);
+        KS_PAR(i, k) ws->Minv[i * LD + i] += reg;
+        KS_SYNC();
+    }
+    return finite(fro) && finite(frog);
 }
 
-// out = A v for a row-major k x k block (collective: one row per lane)
-KS_FN inline void matvec(const double* A, const double* v, int k, double* out) {
-    KS_PAR(i, k) out[i] = dots(A + i * M, 1, v, 1, k);
+// Mi = Minv^{-1} (Gauss-Jordan on [Minv | I]).  Collective; false when singular.
+KS_BIG inline bool invert_minv(Scratch* ws, int k) {
+    KS_PAR2(i, j, k, 2 * k) { ws->X0[i * LW + j] = (j < k) ? ws->Minv[i * LD + j] : ((j - k == i) ? 1.0 : 0.0); } KS_END2
     KS_SYNC();
+    const double* X = gauss_jordan(ws, k, 2 * k);
+    if (!X) return false;
+    KS_PAR2(i, j, k, k) { ws->Mi[i * LD + j] = X[i * LW + k + j]; } KS_END2
+    KS_SYNC();
+    return true;
 }
 
 // =================================================================================
@@ -468,7 +544,8 @@ KS_BIG inline void tr_solve(dd4ml_state* st, int mode, bool f32, Scratch* ws) {
     const double c_s0 = KS_CLOCK();
     const double gn = rT((st->norm_inf[0] != 0.0) ? st->ginf[0] : dsqrt(gg), f32);   // gnT
     const double gam = st->gamma[0];
-    KS_SYNC();                          // all lanes hold the inputs before the master resets the report
+    const bool dogleg = st->dogleg[0] != 0.0;
+    KS_SYNC();                          // all threads hold the inputs before the master resets the report
     KS_PAR(i, MS) { st->cS[i] = 0.0; st->cY[i] = 0.0; }
     KS_MASTER {
         st->cyc_eigh[0] = st->cyc_newton[0] = st->jacobi_sweeps[0] = 0.0;
@@ -496,6 +573,7 @@ KS_BIG inline void tr_solve(dd4ml_state* st, int mode, bool f32, Scratch* ws) {
 #define KS_FAIL(code) { KS_MASTER { st->err[0] = (code); st->solve_valid[0] = 0.0; } KS_SYNC(); return; }
 
     double pred, pp, gp, cg, lam = 0.0;   // the step: p = cg g + lam Psi wv
+    double* wv = ws->vec + 2 * M;
     if (k == 0) {  // optimizer_utils.py:197-215
         const double delT = rT(delta, f32);
         const double scale = rT(rT(ddiv(1.0, gn), f32) * delT, f32);  // python: delta / gn  ==  gn.reciprocal() * delta
@@ -505,61 +583,45 @@ KS_BIG inline void tr_solve(dd4ml_state* st, int mode, bool f32, Scratch* ws) {
         gp = cg * gg;
         KS_MASTER st->case_id[0] = DD4ML_CASE_FIRST_ORDER;
     } else {
-        build_compact(st, ws);
-        double* b = ws->b;
+        double *b = ws->vec, *x = ws->vec + M, *Gw = ws->vec + 3 * M, *z = ws->vec + 4 * M;
         KS_PAR(i, k) { const int pi = (int)st->order[i]; b[i] = st->Yg[pi] - gam * st->Sg[pi]; }  // Psi^T g
-        KS_SYNC();
-        bool ok = finite(gg) && finite(delta) && finite(gam);
-        KS_LOOP
-        for (int i = 0; i < k; ++i) {
-            ok = ok && finite(b[i]);
-            KS_LOOP
-            for (int j = 0; j < k; ++j) ok = ok && finite(ws->G[i * M + j]) && finite(ws->Minv[i * M + j]);
-        }
-        if (!ok) KS_FAIL(DD4ML_ERR_NONFINITE)
+        const bool okm = build_compact(st, ws);                 // (its barriers publish b)
+        if (!(okm && finite(gg) && finite(delta) && finite(gam) && finite(dotk(b, b, k)))) KS_FAIL(DD4ML_ERR_NONFINITE)
         if (delta < 0) KS_FAIL(DD4ML_ERR_NEG_DELTA)
 
-        // ---- OBS (obs.py:61-95) ----
-        double *R = ws->R, *LU = ws->LU, *MR = ws->MR, *RMR = ws->RMR, *U = ws->U, *D = ws->D, *RinvU = ws->RinvU;
-        if (!chol_upper(ws->G, k, R)) KS_FAIL(DD4ML_ERR_CHOLESKY)
-        KS_PAR2(i, j, k) {
-            LU[i * M + j] = ws->Minv[i * M + j];
-            MR[i * M + j] = R[j * M + i];          // right-hand sides R^T
-        } KS_END2
-        KS_SYNC();
-        if (!lu_factor(LU, k, ws->piv)) KS_FAIL(DD4ML_ERR_SINGULAR)
-        lu_solve_cols(LU, ws->piv, k, MR, M, k);    // MR = Minv \ R^T
-        KS_PAR2(i, j, k) { RMR[i * M + j] = dots(R + i * M, 1, MR + j, M, k); } KS_END2
-        KS_SYNC();
-        KS_PAR2(i, j, k) {
-            if (i < j) {
-                const double s = 0.5 * (RMR[i * M + j] + RMR[j * M + i]);
-                RMR[i * M + j] = RMR[j * M + i] = s;
-            }
-        } KS_END2
+        // ---- OBS (obs.py:61-95): eigen-decomposition of R Minv^{-1} R^T, R^T R = Psi^T Psi ----
+        if (!chol_aug(ws, k)) KS_FAIL(DD4ML_ERR_CHOLESKY)
+        if (!invert_minv(ws, k)) KS_FAIL(DD4ML_ERR_SINGULAR)
+        mm(ws->T, LD, ws->Mi, LD, 1, ws->R, 1, LD, k, k, k);   // T = Minv^{-1} R^T
+        mm(ws->J1, LD, ws->R, LD, 1, ws->T, LD, 1, k, k, k);   // R Minv^{-1} R^T
+        KS_PAR2(i, j, k, k) { ws->J0[i * LD + j] = 0.5 * (ws->J1[i * LD + j] + ws->J1[j * LD + i]); } KS_END2
         KS_SYNC();
         const double c_e0 = KS_CLOCK();
-        const int sweeps = jacobi_eigh(RMR, k, D, U, ws);
+        double *A, *V;
+        const int sweeps = jacobi_core(ws, k, &A, &V);
         KS_MASTER { st->jacobi_sweeps[0] = sweeps; st->cyc_eigh[0] = KS_CLOCK() - c_e0; }
         double* Lam = ws->Ld;               // Lambda, a as T values held in doubles (+ float copies for T = float)
         double* a = ws->Ad;
         const double tolT = rT(OBS_TOL, f32), gamT = rT(gam, f32), delT = rT(delta, f32);
-        KS_PAR(c, k) {  // RinvU[:, c] = R \ U[:, c];  a_c = (R^{-1} U)[:, c] . Psi^T g
+        KS_PAR(c, k) {  // eigenvalue c -> ascending rank r, sign convention, a_r = u_r . (R^-T Psi^T g)
+            const double wc = A[c * LD + c];
+            int r = 0, im = 0;
+            double best = -1.0;
             KS_LOOP
-            for (int r = k - 1; r >= 0; --r) {
-                double s = U[r * M + c];
-                KS_LOOP
-                for (int j = r + 1; j < k; ++j) s -= R[r * M + j] * RinvU[j * M + c];
-                RinvU[r * M + c] = ddiv(s, R[r * M + r]);
+            for (int i = 0; i < k; ++i) {
+                const double wi = A[i * LD + i], vi = fabs(V[i * LD + c]);
+                r += (wi < wc || (wi == wc && i < c)) ? 1 : 0;
+                if (vi > best) { best = vi; im = i; }
             }
-            const double s = dots(RinvU + c, M, b, 1, k);
-            ws->ad[c] = s;
-            a[c] = rT(s, f32);
-            double L = rT(rT(D[c], f32) + gamT, f32);
+            double s = dots(V + c, LD, ws->R + k, LD, k);
+            if (V[im * LD + c] < 0.0) s = -s;
+            ws->ad[r] = s;
+            a[r] = rT(s, f32);
+            double L = rT(rT(wc, f32) + gamT, f32);
             if (fabs(L) < tolT) L = 0.0;
-            Lam[c] = L;
-            ws->Af[c] = (float)a[c];
-            ws->Lf[c] = (float)L;
+            Lam[r] = L;
+            ws->Af[r] = (float)a[r];
+            ws->Lf[r] = (float)L;
         }
         KS_SYNC();
         const double gpgp = dotk(ws->ad, ws->ad, k);
@@ -604,22 +666,26 @@ KS_BIG inline void tr_solve(dd4ml_state* st, int mode, bool f32, Scratch* ws) {
         const double tau = tauT;
         KS_MASTER st->tau[0] = tau;
         // SMW step exactly as coded (obs.py:175-182): p_b = -g/tau + Psi (tau Minv + G)^{-1} Psi^T g
-        double *W = ws->W, *wv = ws->wv, *x = ws->x, *z = ws->z, *Gw = ws->Gw;
-        KS_PAR2(i, j, k) { W[i * M + j] = tau * ws->Minv[i * M + j] + ws->G[i * M + j]; } KS_END2
-        KS_PAR(i, k) { wv[i] = b[i]; x[i] = b[i]; }
+        KS_PAR2(i, j, k, k + 1) {
+            ws->X0[i * LW + j] = (j < k) ? tau * ws->Minv[i * LD + j] + ws->G[i * LD + j] : b[i];
+        } KS_END2
         KS_SYNC();
-        if (!lu_factor(W, k, ws->pw)) KS_FAIL(DD4ML_ERR_SINGULAR)
-        KS_PAR(c, 2) {
-            if (c == 0) lu_solve_vec(W, ws->pw, k, wv, 1);     // wv = (tau Minv + G) \ Psi^T g
-            else lu_solve_vec(LU, ws->piv, k, x, 1);           // x  = Minv \ Psi^T g
+        const double* X = gauss_jordan(ws, k, k + 1);       // wv = (tau Minv + G) \ Psi^T g
+        if (!X) KS_FAIL(DD4ML_ERR_SINGULAR)
+        KS_PAR(i, 2 * k) {
+            if (i < k) wv[i] = X[i * LW + k];
+            else x[i - k] = dots(ws->Mi + (i - k) * LD, 1, b, 1, k);      // x = Minv \ Psi^T g
         }
         KS_SYNC();
-        matvec(ws->G, wv, k, Gw);
-        KS_PAR(i, k) z[i] = Gw[i];
+        mm(Gw, 1, ws->G, LD, 1, wv, 1, 0, k, 1, k);         // G wv
+        mm(z, 1, ws->Mi, LD, 1, Gw, 1, 0, k, 1, k);         // z = Minv \ (G wv)
+        KS_PAR(q, 6) {  // b.x  b.wv  wv.Gw  b.z  Gw.x  Gw.z   (vec blocks: 0 b, 1 x, 2 wv, 3 Gw, 4 z)
+            const int ia = (0x330200 >> (4 * q)) & 15, ib = (0x414321 >> (4 * q)) & 15;
+            ws->dot6[q] = dots(ws->vec + ia * M, 1, ws->vec + ib * M, 1, k);
+        }
         KS_SYNC();
-        lu_solve_cols(LU, ws->piv, k, z, 1, 1);     // z  = Minv \ (G wv)
-        const double bx = dotk(b, x, k), bw = dotk(b, wv, k), wGw = dotk(wv, Gw, k);
-        const double bz = dotk(b, z, k), gwx = dotk(Gw, x, k), gwz = dotk(Gw, z, k);
+        const double bx = ws->dot6[0], bw = ws->dot6[1], wGw = ws->dot6[2];
+        const double bz = ws->dot6[3], gwx = ws->dot6[4], gwz = ws->dot6[5];
         const double cgb = rT(ddiv(-1.0, tauT), f32);
 #define KS_PP(c_, l_) ((c_) * (c_) * gg + 2.0 * (c_) * (l_) * bw + (l_) * (l_) * wGw)
 #define KS_GP(c_, l_) ((c_) * gg + (l_) * bw)
@@ -629,7 +695,7 @@ KS_BIG inline void tr_solve(dd4ml_state* st, int mode, bool f32, Scratch* ws) {
         cg = cgb;
         lam = 1.0;
         double branch = 0.0;
-        if (st->dogleg[0] != 0.0 && gBg > 0.0) {
+        if (dogleg && gBg > 0.0) {
             const double alpha = ddiv(gn * gn, gBg);
             const double cc = (alpha * dsqrt(gg) >= delta) ? -ddiv(delta, gn) : -alpha;
             const double pb_norm = dsqrt(KS_PP(cgb, 1.0));
@@ -684,7 +750,7 @@ KS_BIG inline void tr_solve(dd4ml_state* st, int mode, bool f32, Scratch* ws) {
     }
     KS_PAR(i, k) {
         const int pi = (int)st->order[i];
-        const double c = lam * ws->wv[i];
+        const double c = lam * wv[i];
         st->cY[pi] = c;
         st->cS[pi] = -gam * c;
     }
@@ -728,19 +794,20 @@ KS_BIG inline bool lsr1_try_update(dd4ml_state* st, Scratch* ws) {
         us = sy - gam * ss;
         uu = yy - 2.0 * gam * sy + gam * gam * ss;
     } else {
-        build_compact(st, ws);
-        double *bs = ws->bs, *by = ws->by, *x = ws->x, *LU = ws->LU, *Gx = ws->Gw;
+        double *bs = ws->vec, *by = ws->vec + M, *x = ws->vec + 2 * M, *Gx = ws->vec + 3 * M;
         KS_PAR(i, k) {
             const int pi = (int)st->order[i];
             bs[i] = st->c_Ys[pi] - gam * st->c_Ss[pi];   // Psi^T s
             by[i] = st->c_Yy[pi] - gam * st->c_Sy[pi];   // Psi^T y
-            x[i] = bs[i];
         }
-        KS_PAR2(i, j, k) { LU[i * M + j] = ws->Minv[i * M + j]; } KS_END2
+        build_compact(st, ws);
+        KS_PAR2(i, j, k, k + 1) { ws->X0[i * LW + j] = (j < k) ? ws->Minv[i * LD + j] : bs[i]; } KS_END2
         KS_SYNC();
-        if (!lu_factor(LU, k, ws->piv)) { KS_MASTER st->err[0] = DD4ML_ERR_SINGULAR; KS_SYNC(); return false; }
-        lu_solve_cols(LU, ws->piv, k, x, 1, 1);          // x = Minv \ Psi^T s
-        matvec(ws->G, x, k, Gx);
+        const double* X = gauss_jordan(ws, k, k + 1);    // x = Minv \ Psi^T s
+        if (!X) { KS_MASTER st->err[0] = DD4ML_ERR_SINGULAR; KS_SYNC(); return false; }
+        KS_PAR(i, k) x[i] = X[i * LW + k];
+        KS_SYNC();
+        mm(Gx, 1, ws->G, LD, 1, x, 1, 0, k, 1, k);
         const double bsx = dotk(bs, x, k);
         us = sy - gam * ss - bsx;
         uu = yy + gam * gam * ss + dotk(x, Gx, k) - 2.0 * gam * sy - 2.0 * dotk(by, x, k) + 2.0 * gam * bsx;
@@ -764,7 +831,7 @@ KS_BIG inline bool lsr1_try_update(dd4ml_state* st, Scratch* ws) {
         KS_LOOP
         while (newspare < MS && ((used >> newspare) & 1u)) ++newspare;
     }
-    KS_SYNC();                          // every lane has read the old ring before it changes
+    KS_SYNC();                          // every thread has read the old ring before it changes
     KS_PAR(i, k) {                      // Gram rows/columns of the new pair against the live pairs
         const int pj = (int)st->order[i];
         if (!(k >= m && i == 0)) {      // (the dropped pair's entries are dead)
@@ -814,18 +881,18 @@ KS_BIG inline void coefs_B_or_smw(dd4ml_state* st, Scratch* ws, bool smw) {
     KS_SYNC();
     if (k == 0) return;
     build_compact(st, ws);
-    double *x = ws->x, *A = ws->W;
-    KS_PAR(i, k) { const int pi = (int)st->order[i]; x[i] = st->Yg[pi] - gam * st->Sg[pi]; }
-    KS_PAR2(i, j, k) {
-        A[i * M + j] = smw ? tau * ws->Minv[i * M + j] + ws->G[i * M + j] : ws->Minv[i * M + j];
+    KS_PAR2(i, j, k, k + 1) {
+        const int pi = (int)st->order[i];
+        ws->X0[i * LW + j] = (j == k) ? st->Yg[pi] - gam * st->Sg[pi]
+                                      : (smw ? tau * ws->Minv[i * LD + j] + ws->G[i * LD + j] : ws->Minv[i * LD + j]);
     } KS_END2
     KS_SYNC();
-    if (!lu_factor(A, k, ws->pw)) { KS_MASTER st->err[0] = DD4ML_ERR_SINGULAR; KS_SYNC(); return; }
-    lu_solve_cols(A, ws->pw, k, x, 1, 1);
+    const double* X = gauss_jordan(ws, k, k + 1);
+    if (!X) { KS_MASTER st->err[0] = DD4ML_ERR_SINGULAR; KS_SYNC(); return; }
     KS_PAR(i, k) {
         const int pi = (int)st->order[i];
-        st->cY[pi] = x[i];
-        st->cS[pi] = -gam * x[i];
+        st->cY[pi] = X[i * LW + k];
+        st->cS[pi] = -gam * X[i * LW + k];
     }
     KS_SYNC();
 }

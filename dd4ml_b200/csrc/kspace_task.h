@@ -1,4 +1,4 @@
-// The k-space kernel (k_kspace.cu) and its launch: ONE warp that runs the O(k^2)-input part of a
+// The k-space kernel (k_kspace.cu) and its launch: ONE CTA (1 or 4 warps) that runs the O(k^2)-input part of a
 // trust-region step (L-SR1 update chain, OBS / dogleg solve, ratio test bookkeeping) on the device
 // state block, right behind the streaming reduction kernel that filled the block's reduction fields.
 // It is launched with programmatic dependent launch: the reduction kernels signal
@@ -25,4 +25,4 @@ struct KTask {
 };
 
 // enqueue the k-space kernel for `state` behind the work already in `stream`; returns a cudaError_t
-int dd4ml_ks_launch(double* state, const KTask& task, cudaStream_t stream);
+int dd4ml_ks_launch(double* state, const KTask& task, cudaStream_t stream, int kcap);

@@ -49,11 +49,11 @@ void hostshim_secular(int mode, double x0, const double* Lam, const double* a, i
     }
 }
 int hostshim_eigh(const double* A, int k, double* w, double* V) {
-    double a[ks::M * ks::M], v[ks::M * ks::M], ww[ks::M];
+    double a[ks::M * ks::LD], v[ks::M * ks::LD], ww[ks::M];
     ks::Scratch ws;
-    for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) a[i * ks::M + j] = A[i * k + j];
-    ks::jacobi_eigh(a, k, ww, v, &ws);
-    for (int i = 0; i < k; ++i) { w[i] = ww[i]; for (int j = 0; j < k; ++j) V[i * k + j] = v[i * ks::M + j]; }
-    return 0;
+    for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) a[i * ks::LD + j] = A[i * k + j];
+    const int sweeps = ks::jacobi_eigh(a, k, ww, v, &ws);
+    for (int i = 0; i < k; ++i) { w[i] = ww[i]; for (int j = 0; j < k; ++j) V[i * k + j] = v[i * ks::LD + j]; }
+    return sweeps;
 }
 }
