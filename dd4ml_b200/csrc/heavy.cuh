@@ -7,6 +7,7 @@ namespace {
 // Loader handed to Op::body_l: data straight from global memory (register staged).  The TMA
 // kernel passes a SmemLoader with the same interface (tma.cuh).
 struct GlobalLoader {
+    static constexpr bool kStaged = false;  // every load is a memory round trip: ops issue them all up front
     template <int V, class T>
     __device__ __forceinline__ void get(int, const T* __restrict__ gptr, int64_t i, bool rw, Raw<V, T>& r) const {
         if (rw) ldr_rw<V, T>(r, gptr, i); else ldr_ro<V, T>(r, gptr, i);

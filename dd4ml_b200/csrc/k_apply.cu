@@ -6,7 +6,7 @@ namespace {
 template <class HT, class VT, class WT, int KMAX>
 struct ApplyOp {
     static constexpr int NRED = 1;
-    static constexpr int F = 2, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4;
+    static constexpr int F = 2, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4, TMA_SPLIT = 1;
     __host__ __device__ static constexpr bool is_max(int) { return true; }
     dd4ml_state* st;
     const VT* g;

@@ -6,9 +6,10 @@ namespace {
 template <class HT, class VT, class WT, int KMAX>
 struct LssrBeginOp {
     static constexpr int NRED = 7 + 6 * KMAX;
-    // KMAX = 10: 24 streams x 4 KB leave two stages in the ring; half tiles (4 stages) measured 0.50 -> 0.59
-    // of peak here, but lose on the ops with fewer streams (twice the loop overhead per element)
-    static constexpr int F = 4, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = KMAX > 6 ? 2 : 4;
+    // KMAX = 10: 24 streams x 4 KB would leave two stages in the ring.  Two consumer groups of four warps take
+    // alternate 2 KB-per-stream tiles instead: four stages, and a thread still owns 4 consecutive elements
+    // (67 accumulators: one float32 -> float64 conversion per accumulator per 4 elements, see heavy.cuh)
+    static constexpr int F = 4, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4, TMA_SPLIT = KMAX > 6 ? 2 : 1;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 1; }
     dd4ml_state* st;
     const WT* w;
@@ -49,13 +50,15 @@ struct LssrBeginOp {
         Raw<V, WT> wr, owr;
         Raw<V, VT> gr, pgr;
         PairRegs<V, HT, KMAX> pr;
+        constexpr bool kF32Tiles = KMAX > 6 && BothF32<HT, VT>::value && BothF32<WT, WT>::value && V > 1;
+        constexpr bool kJustInTime = kF32Tiles && L::kStaged;   // shared-memory operands: load pair j when it is used
         l.template get<V, WT>(0, w, i, false, wr);
         l.template get<V, VT>(1, g, i, false, gr);
         if (pair) {
             l.template get<V, WT>(2, old_w, i, true, owr);
             l.template get<V, VT>(3, prev_g, i, true, pgr);
         }
-        pr.load(l, F, S, Y, ld, sl, i);
+        if constexpr (!kJustInTime) pr.load(l, F, S, Y, ld, sl, i);
         double wv[V], gv[V], sv[V], yv[V];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -78,13 +81,17 @@ struct LssrBeginOp {
                 acc[6] += yv[e] * gv[e];
             }
         }
-        if constexpr (KMAX > 6 && BothF32<HT, VT>::value && BothF32<WT, WT>::value && V > 1) {
+        if constexpr (kF32Tiles) {
             float sf[V], yf[V];
 #pragma unroll
             for (int e = 0; e < V; ++e) { sf[e] = pair ? (float)sv[e] : 0.f; yf[e] = pair ? (float)yv[e] : 0.f; }   // exact: sv, yv are float32 values
 #pragma unroll
             for (int j = 0; j < KMAX; ++j)
                 if (sl.live(j)) {
+                    if constexpr (kJustInTime) {
+                        l.template get<V, HT>(F + j, S, i, false, pr.s[j]);
+                        l.template get<V, HT>(F + KMAX + j, Y, i, false, pr.y[j]);
+                    }
                     acc[7 + j] += (double)dot32<V>(pr.s[j].x, gr.x);
                     acc[7 + KMAX + j] += (double)dot32<V>(pr.y[j].x, gr.x);
                     if (pair) {

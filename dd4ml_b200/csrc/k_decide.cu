@@ -6,7 +6,7 @@ namespace {
 template <class HT, class VT, class WT, int KMAX, bool MEM>
 struct DecideOp {
     static constexpr int NRED = 5 + 4 * KMAX;
-    static constexpr int F = 3, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4;
+    static constexpr int F = 3, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4, TMA_SPLIT = 1;
     __host__ __device__ static constexpr bool is_max(int j) { return j == 4; }
     dd4ml_state* st;
     const void* loss;
@@ -151,7 +151,7 @@ struct DecideOp {
 template <class HT, class VT, int KMAX>
 struct UpdateOp {
     static constexpr int NRED = 3 + 4 * KMAX;
-    static constexpr int F = 2, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4;
+    static constexpr int F = 2, NS_MAX = F + 2 * KMAX, TMA_CW = 8, TMA_PW = 4, TMA_V = 4, TMA_SPLIT = 1;
     __host__ __device__ static constexpr bool is_max(int) { return false; }
     dd4ml_state* st;
     const VT* s_in;

@@ -55,7 +55,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // compile-time offset sid * TILE * 4 of its stage: one base register + immediates, no lookups.
 template <int STREAM_BYTES>
 struct SmemLoader {
-    const unsigned char* mine;   // stage base + 4 V * threadIdx.x
+    static constexpr bool kStaged = true;   // data already on chip: ops may load just in time
+    const unsigned char* mine;   // stage base + 4 V * (thread index within its consumer group)
     template <int V, class T>
     __device__ __forceinline__ void get(int sid, const T*, int64_t, bool, Raw<V, T>& r) const {
         static_assert((V == 4 || V == 2) && sizeof(T) == 4, "the smem ring holds fp32 streams, read 4 or 2 elements per thread");
@@ -113,8 +114,13 @@ template <class Op, int CW, int PW>
 __global__ void __launch_bounds__((CW + PW) * 32, 1) tma_kernel(Op op, int64_t n, double* ws, int nstage) {
     static_assert(PW == 1 || (PW == 4 && CW == 8), "register hand-over needs whole warpgroups");
     constexpr int CT = CW * 32;       // consumer threads
-    constexpr int V = Op::TMA_V;      // elements per consumer thread per tile (4, or 2 when a 4 KB-per-stream
-    constexpr int TILE = CT * V;      //  stage would leave the 200 KB ring with two stages: KMAX = 10)
+    constexpr int V = Op::TMA_V;      // elements per consumer thread per tile
+    // SPLIT consumer groups take alternate tiles: a tile is then GT x V elements, i.e. the stage shrinks
+    // (more stages in the 200 KB ring) while a thread still owns V consecutive elements -- what the ops
+    // with 60+ accumulators want (one float32 -> float64 conversion per accumulator per V elements)
+    constexpr int SPLIT = Op::TMA_SPLIT;
+    constexpr int GT = CT / SPLIT;
+    constexpr int TILE = GT * V;
     constexpr int STREAM_BYTES = TILE * 4;
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) uint64_t full[MAX_STAGES];
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__((CW + PW) * 32, 1) tma_kernel(Op op, int64_t n
             nlive += p ? 1 : 0;
         }
         s_nlive = nlive;
-        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW / SPLIT); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -161,19 +167,21 @@ __global__ void __launch_bounds__((CW + PW) * 32, 1) tma_kernel(Op op, int64_t n
     if (op.active() && !producer) {
         if (tma) {
             const int64_t ntiles = (nv4 + TILE - 1) / TILE;
-            int stg = 0;
+            const int grp = (int)threadIdx.x / GT, lt = (int)threadIdx.x - grp * GT;
+            int stg = grp;            // the CTA's tiles in order use stages 0, 1, 2 ...; this group takes every SPLIT-th
             uint32_t ph = 0;
-            const unsigned char* mine = ring + threadIdx.x * (4 * V);
-            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const unsigned char* mine = ring + lt * (4 * V);
+            for (int64_t t = blockIdx.x + (int64_t)grp * gridDim.x; t < ntiles; t += (int64_t)SPLIT * gridDim.x) {
                 mbar_wait(&full[stg], ph);
-                const int64_t i0 = t * TILE + (int64_t)threadIdx.x * V;
+                const int64_t i0 = t * TILE + (int64_t)lt * V;
                 if (i0 < nv4) {
                     SmemLoader<STREAM_BYTES> ld{mine + stg * STAGE_BYTES};
                     op.template body_l<V>(ld, i0, acc);
                 }
                 __syncwarp();
                 if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stg]);
-                if (++stg == nstage) { stg = 0; ph ^= 1u; }
+                stg += SPLIT;
+                if (stg >= nstage) { stg -= nstage; ph ^= 1u; }
             }
         } else {
             const int64_t tid = (int64_t)blockIdx.x * CT + threadIdx.x;
@@ -224,10 +232,11 @@ inline int launch_heavy(Op op, int64_t n, bool vec, double* ws, int per_sm, int 
                         cudaStream_t s) {
     static_assert(Op::NRED <= MAXRED, "too many fused reductions");
     (void)stage_bytes;   // the ring is laid out for all NS_MAX streams of the op
-    constexpr int TILE = Op::TMA_CW * 32 * Op::TMA_V;
+    constexpr int TILE = Op::TMA_CW * 32 / Op::TMA_SPLIT * Op::TMA_V;
     constexpr int STAGE_BYTES = Op::NS_MAX * TILE * 4;
     int nstage = SMEM_BUDGET / STAGE_BYTES;
     if (nstage > MAX_STAGES) nstage = MAX_STAGES;
+    static_assert(SMEM_BUDGET / STAGE_BYTES >= Op::TMA_SPLIT, "every consumer group needs a stage of its own");
     const bool want = tma_mode() == 1 || (tma_mode() == 0 && tma_default);
     if (!want || !vec || nstage < 2 || n < tma_min_n()) return launch(op, n, vec, ws, per_sm, s);
     const int64_t ntiles = ((n & ~(int64_t)3) + TILE - 1) / TILE;
@@ -247,11 +256,12 @@ inline int launch_sel(Op op, int64_t n, bool vec, double* ws, int per_sm, int st
 
 template <int K> using KC = std::integral_constant<int, K>;
 
-// calls run(KC<4|6|MAXM>) for FAST combinations, run(KC<MAXM>) otherwise
+// calls run(KC<4|6|8|MAXM>) for FAST combinations, run(KC<MAXM>) otherwise
 #define DD4ML_RUN_K(FAST, kcap, run)                           \
     if constexpr (FAST) {                                      \
         if ((kcap) <= 4) return run(KC<4>{});                  \
         if ((kcap) <= 6) return run(KC<6>{});                  \
+        if ((kcap) <= 8) return run(KC<8>{});                  \
     }                                                          \
     return run(KC<DD4ML_MAXM>{});
 
