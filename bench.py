@@ -315,6 +315,11 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
             finally:
                 lib.cdll.dd4ml_debug_kspace(1)
                 ds.state.copy_(state_copy)
+        if name == "dd4ml_tr_apply":
+            # the direction pass only streams the pairs whose coefficients are non-zero (a Cauchy-point or
+            # first-order step streams none): count what this launch really read
+            full = ds.read(full=True)
+            kk = sum(1 for sl in (int(o) for o in full.order[:kk]) if full.cS[sl] != 0.0 or full.cY[sl] != 0.0)
         byt = algorithmic_bytes(name, n, kk)
         out[name] = {"n": n, "k": kk, "ms": ms, "bytes": byt, "achieved": byt / ms / 1e6,
                      "frac": byt / ms / 1e6 / peak_gbs, "ms_entry_with_kspace_kernel": ms_entry,
@@ -353,7 +358,7 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
 
 
 # ---------------------------------------------------------------------------------- measurement of one job
-def measure(job, args, world, device, flush, rank, local, full=True):
+def measure(job, args, world, device, flush, rank, local, full=True, make_job=None):
     """Warm-up, the timed region (inputs resident), the end-to-end region (host batches), and one
     profiled pass (CUDA events around every own launch, every closure, every collective)."""
     import torch.distributed as dist
@@ -387,28 +392,38 @@ def measure(job, args, world, device, flush, rank, local, full=True):
     spec = CONFIGS[job.name]
     value = world * args.steps / (ms / 1e3)
 
-    # ---- end-to-end: host batch -> device every step, loss read back every step (the call a user makes)
+    # ---- end-to-end: host batch -> device every step, loss read back every step (the call a user makes).
+    # The work per outer iteration depends on where the run is on its trajectory (line-search evaluations),
+    # so the end-to-end region runs on a FRESH job with the same seeds: same warm-up, same outer iterations
+    # as the resident region above.
+    ejob = make_job() if make_job is not None else job
     host_loss = torch.empty((), dtype=torch.float64).pin_memory()
-    if len(job.host_batch) == 2 and job.name != "pinn_apts_p":
+    feed = None
+    if len(ejob.host_batch) == 2 and ejob.name != "pinn_apts_p":
         # the public feed: pinned host batches through HostBatchPrefetcher -- the copy of the next step's
         # batch runs on a side stream under the current step; one H2D copy per step
         import itertools
         from dd4ml_b200.dataloaders import HostBatchPrefetcher
-        feed = iter(HostBatchPrefetcher(itertools.repeat(job.host_batch), device))
+        feed = iter(HostBatchPrefetcher(itertools.repeat(ejob.host_batch), device))
         nxt = lambda: next(feed)  # noqa: E731
     else:
-        nxt = lambda: job.upload(job.host_batch)  # noqa: E731
+        nxt = lambda: ejob.upload(ejob.host_batch)  # noqa: E731
 
     def step_e2e(i):
-        loss = job.step(nxt())
+        loss = ejob.step(nxt())
         host_loss.copy_(loss.detach().double(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    for i in range(2):
+    for i in range(args.warmup if ejob is not job else 2):
         step_e2e(i)
     ms_e2e, _ = timed_region(step_e2e, args.steps, world, device, flush)
     e2e = {"value": world * args.steps / (ms_e2e / 1e3), "unit": spec["unit"],
-           "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in job.host_batch),
-           "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps}
+           "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in ejob.host_batch),
+           "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
+           "iterations": "the same outer iterations as `value` (fresh job, same seeds and warm-up)"
+                         if ejob is not job else "the outer iterations after the resident region"}
+    if ejob is not job:
+        del ejob, feed, nxt
+        torch.cuda.empty_cache()
 
     # ---- profiled pass: per-kernel device times inside the step, closures, collectives
     lib.prof, GraphedEval.PROF, apts_base.COMM_PROF = {}, [], []
@@ -672,7 +687,8 @@ def main():
 
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
     job = build_job(args.config, device, world, rank, labels=args.labels)
-    res, clocks, dominant = measure(job, args, world, device, flush, rank, local)
+    res, clocks, dominant = measure(job, args, world, device, flush, rank, local,
+                                    make_job=lambda: build_job(args.config, device, world, rank, labels=args.labels))
 
     # ---- equal-work scaling diagnostic: the same workload with learnable (teacher) labels
     teacher = None

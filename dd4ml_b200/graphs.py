@@ -8,8 +8,9 @@ Python/dispatcher time), so it is captured once into a CUDA graph and replayed -
 model's forward/backward kernels themselves are untouched.
 
 Inputs are captured by address.  When the caller keeps passing the same tensors the graph
-reads them in place; when the addresses change between calls the evaluator switches to a
-private static copy (one ``copy_`` per call).  Anything that cannot be captured (data
+reads them in place; a small ring of batch buffers (``HostBatchPrefetcher``: two) gets one graph
+per buffer, all in one memory pool; once more than ``MAX_ADDRESSES`` distinct addresses have been
+seen the evaluator switches to a private static copy (one ``copy_`` per call).  Anything that cannot be captured (data
 dependent Python control flow in the model, unsupported ops) falls back to the eager
 PyTorch path for that shape -- this only concerns the PyTorch closure, never the
 dd4ml_b200 kernels.
@@ -21,6 +22,7 @@ import os
 import torch
 
 ENABLED = os.environ.get("DD4ML_B200_CUDA_GRAPHS", "1") != "0"
+MAX_ADDRESSES = 3     # in-place graphs per batch shape before falling back to a private input copy
 
 
 class _Entry:
@@ -66,7 +68,7 @@ class GraphedEval:
         return (tuple(inputs.shape), inputs.dtype, tuple(inputs.stride()), tuple(labels.shape), labels.dtype,
                 tuple(labels.stride()), self.flat.version, self.model.training)
 
-    def _capture(self, inputs, labels, private):
+    def _capture(self, inputs, labels, private, pool=None):
         e = _Entry()
         e.private = private
         e.static_in = inputs.clone() if private else inputs
@@ -84,7 +86,7 @@ class GraphedEval:
             for b, v in zip(self.model.buffers(), saved):
                 b.copy_(v)
         e.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(e.graph):
+        with torch.cuda.graph(e.graph, pool=pool):       # graphs of one shape never run concurrently
             e.loss = self._eval(e.static_in, e.static_lab)
         self.captures += 1
         return e
@@ -98,13 +100,17 @@ class GraphedEval:
             self.cache.clear()                   # parameters were re-bound: drop every stale graph
         if key in self.failed:
             return self._eval(inputs, labels)
-        e = self.cache.get(key)
+        ents = self.cache.setdefault(key, [])
+        ip, lp = inputs.data_ptr(), labels.data_ptr()
+        e = next((x for x in ents if not x.private and x.static_in.data_ptr() == ip and x.static_lab.data_ptr() == lp),
+                 None)
+        if e is None:
+            e = next((x for x in ents if x.private), None)     # (only exists once the address budget is spent)
         try:
             if e is None:
-                e = self.cache[key] = self._capture(inputs, labels, private=False)
-            elif not e.private and (e.static_in.data_ptr() != inputs.data_ptr()
-                                    or e.static_lab.data_ptr() != labels.data_ptr()):
-                e = self.cache[key] = self._capture(inputs, labels, private=True)   # addresses move: own copy
+                pool = ents[0].graph.pool() if ents else None
+                e = self._capture(inputs, labels, private=len(ents) >= MAX_ADDRESSES, pool=pool)
+                ents.append(e)
         except Exception:  # noqa: BLE001  (capture unsupported for this model: eager PyTorch closure)
             self.failed.add(key)
             torch.cuda.synchronize()
