@@ -17,7 +17,7 @@ def main(path, last=None):
         m = re.search(r"(stream_kernel|tma_kernel)<.*?::(\w+Op)<([^>]*)>", name)
         if m:
             key = f"dd4ml_b200 {m.group(1)}<{m.group(2)}<{m.group(3)}>>"
-        elif re.search(r"<unnamed>::(state_\w+|gather_kernel|seg_copy_kernel)", name):
+        elif re.search(r"<unnamed>::(state_\w+|gather_kernel|seg_copy_kernel|kspace_kernel|combine_kernel|gather_rows_kernel)", name):
             key = "dd4ml_b200 " + re.search(r"<unnamed>::(\w+)", name).group(1)
         else:
             key = "torch  " + re.sub(r"[<(].*", "", name.replace("void ", ""))[:60]

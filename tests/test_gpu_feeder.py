@@ -66,6 +66,34 @@ def test_apts_d_fed_from_device_matches_host_batches():
     assert dev_losses == host_losses
 
 
+def test_apts_d_fed_through_prefetcher_ring_matches_resident_batches():
+    """The closure graphs read the prefetcher's two ring buffers in place (one captured graph per buffer
+    address, dd4ml_b200/graphs.py): different batch contents at a recurring address must be seen."""
+    from dd4ml_b200.dataloaders import HostBatchPrefetcher
+    from dd4ml_b200.graphs import GraphedEval
+    g = load_golden("apts_d_tr_fo_ws1")
+    X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
+    gen = torch.Generator().manual_seed(3)
+    idx = [torch.randperm(X.shape[0], generator=gen)[:48] for _ in range(7)]
+    host = [(X[i].clone().pin_memory(), Y[i].clone().pin_memory()) for i in idx]
+
+    def run(feed):
+        from test_gpu_optimizers import _apts, cfg
+        model = FFNN(36, [12, 12], 10)
+        set_flat(model, torch.from_numpy(g["w0"]))
+        opt = _apts("d", model.to(DEV), "tr", "tr", cfg(), foc=True)
+        losses = [float(opt.step(xb, yb)) for xb, yb in feed]
+        evs = [v for v in vars(opt).values() if isinstance(v, GraphedEval)]
+        return losses, evs
+
+    ring_losses, evs = run(HostBatchPrefetcher(host, DEV, depth=2))
+    res_losses, _ = run((x.to(DEV), y.to(DEV)) for x, y in host)
+    assert ring_losses == res_losses and len(ring_losses) == 7
+    for ev in evs:                                   # two addresses -> two in-place graphs, no private copy
+        for ents in ev.cache.values():
+            assert 1 <= len(ents) <= 2 and not any(e.private for e in ents)
+
+
 def test_host_batch_prefetcher_delivers_every_batch_in_order():
     from dd4ml_b200.dataloaders import HostBatchPrefetcher
     gen = torch.Generator().manual_seed(1)

@@ -155,6 +155,24 @@ def test_apts_d_trajectory_matches_reference(name, glob, loc, so, dog):
     assert rel_err(opt.w, g["w_final"]) < 1e-3
 
 
+@pytest.mark.parametrize("name,glob", [("apts_d_tr_fo_ws8", "tr"), ("apts_d_lssr1_fo_ws8", "lssr1_tr")])
+def test_apts_d_eight_subdomains(name, glob):
+    """8 gloo ranks of the reference, 16 samples each, 8 outer iterations.  TR: the whole run.  LSSR1_TR: ~130
+    strong-Wolfe searches in float32 -- the restatement (subdomains summed in rank order instead of gloo's
+    ring order) follows the reference evaluation for evaluation for the first 4 iterations, then one search
+    takes a different number of evaluations (iteration 5 here, iteration 6 for the CUDA path): the rule used
+    for this case everywhere (tests/test_gpu_multi.py, tools/bench_parity.py) is identity over the first half
+    of the run, radii identical and losses within 1e-3 throughout."""
+    g, opt, losses, deltas, gev = _apts_d(name, glob, glob, False, False)
+    np.testing.assert_allclose(losses, g["loss"], rtol=1e-3)
+    np.testing.assert_allclose(deltas, g["delta"], rtol=1e-12)
+    same = np.isclose(gev, g["grad_evals"], rtol=0, atol=1e-9)
+    if glob == "tr":
+        assert same.all()
+    else:
+        assert (len(same) if same.all() else int(np.argmin(same))) >= len(same) // 2
+
+
 def _owned_indices(model, tensor_ids):
     sizes = [p.numel() for p in model.parameters()]
     offs = np.concatenate([[0], np.cumsum(sizes)])
