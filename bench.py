@@ -742,9 +742,18 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
         return
-    roofline, sweep = (None, None)
+    roofline, sweep, roof_gpt = (None, None, None)
     if not args.no_sweep:
         roofline, sweep = large_n_roofline(device, dominant, peak, peak_src)
+        if world == 1:
+            # the same measurement at the largest BASELINE vector length (gpt-mini, n = 2 719 104: 152 MB per
+            # lssr1_begin launch, above the 126 MB L2): the HBM-bound regime on a real config's size
+            rg, sg = large_n_roofline(device, dominant, peak, peak_src, n=2719104, k=3, iters=50)
+            rg["workload"] = "fp32 n=2719104 (minGPT gpt-mini, BASELINE configs[3]) k=3, launches back to back"
+            rg.pop("traffic", None)
+            roof_gpt = {"roofline": rg, "kernels": {k: {"ms": v["ms"], "frac": v["frac"],
+                                                        "frac_entry_with_kspace_kernel": v["frac_entry_with_kspace_kernel"]}
+                                                    for k, v in sg.items()}}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cargs = argparse.Namespace(steps=60 if args.config in ("ffnn_apts_d", "pinn_apts_p", "deeponet_tr") else 5,
@@ -764,7 +773,7 @@ def main():
                                "optimizer_side_ms_per_step", "profiled_ms_per_step", "allreduce", "p2p_combine",
                                "exchange", "per_rank")},
         "clocks": clocks, "roofline": roofline, "roofline_native": res["roofline_native"],
-        "roofline_sweep": sweep, "cpu_baseline": cpu, "parity_check": parity, "teacher_labels": teacher,
+        "roofline_sweep": sweep, "roofline_gpt_mini_size": roof_gpt, "cpu_baseline": cpu, "parity_check": parity, "teacher_labels": teacher,
         "other_configs": others,
         "final_loss": res["final_loss"], "first_loss": res["first_loss"],
     }

@@ -50,6 +50,7 @@ class GraphedEval:
         self.failed: set = set()
         self.replays = 0
         self.captures = 0
+        self._hot = None      # (inputs, labels, flat version, training, in ptr, lab ptr, entry) of the last replay
 
     # the eager evaluation (also what gets captured)
     def _eval(self, inputs, labels):
@@ -92,6 +93,17 @@ class GraphedEval:
         return e
 
     def _call(self, inputs, labels):
+        # hot path (every evaluation of an outer iteration passes the same batch objects): the replay is the
+        # first device work after a host read, so nothing but these identity checks precedes it
+        hot = self._hot
+        if (hot is not None and hot[0] is inputs and hot[1] is labels and hot[2] == self.flat.version
+                and hot[3] == self.model.training and hot[4] == inputs.data_ptr() and hot[5] == labels.data_ptr()
+                and not inputs.requires_grad):
+            e = hot[6]
+            e.graph.replay()
+            self.flat.rebind_grads()
+            self.replays += 1
+            return e.loss.clone()
         if (not ENABLED or not torch.is_tensor(inputs) or not torch.is_tensor(labels) or inputs.requires_grad
                 or not inputs.is_cuda):
             return self._eval(inputs, labels)
@@ -118,6 +130,9 @@ class GraphedEval:
         if e.private:
             e.static_in.copy_(inputs)
             e.static_lab.copy_(labels)
+            self._hot = None
+        else:
+            self._hot = (inputs, labels, key[-2], key[-1], ip, lp, e)
         e.graph.replay()
         # the replay wrote the gradient into the flat views; a caller may have set p.grad to None
         # (zero_grad(set_to_none=True)) since the capture -- re-establish the views so that
