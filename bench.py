@@ -57,6 +57,7 @@ CONFIGS = {
         "BASELINE configs[0]: DeepONet (n=11712) on the deeponet_sine synthetic operator data, batch 1000, plain TR "
         "second-order (L-SR1 mem 5, OBS), delta 0.1 in [1e-3, 2], float targets + MSE")),
 }
+PER_RANK_BATCH = CONFIGS["ffnn_apts_d"]["batch"]
 
 
 def env_int(name, default):
@@ -130,6 +131,12 @@ def _apts_d(model, crit, device, world, **over):
                   glob_opt=c.glob_opt, glob_opt_hparams=c.glob_opt_hparams, loc_opt=c.loc_opt,
                   loc_opt_hparams=c.loc_opt_hparams, glob_pass=c.glob_pass, foc=c.foc, norm_type=c.norm_type,
                   max_loc_iters=c.max_loc_iters, max_glob_iters=c.max_glob_iters, tol=c.tol, **c.apts_params)
+
+
+def build_optimizer(device, world, rank=None):
+    """(model, optimizer) of the default bench workload: what the diagnostics under tools/ drive."""
+    job = build_job("ffnn_apts_d", device, world, env_int("RANK", 0) if rank is None else rank)
+    return job.model, job.opt
 
 
 def build_job(name, device, world, rank, labels="random", batch=None):
@@ -299,7 +306,17 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
 
     for name, fn in calls.items():
         if name == "dd4ml_tr_apply":
+            # the direction pass streams the pairs whose coefficients are non-zero (a Cauchy-point or first-order
+            # step streams none): give every live pair a coefficient so that the launch reads what
+            # `algorithmic_bytes` counts, whatever the solve on the synthetic memory came out as
             lib.tr_propose(ds.sp, ds.wp, gv.data_ptr(), h.S_ptr, h.Y_ptr, n, h.ld, 0, 0, 1, k, st)
+            full = ds.read(full=True)
+            coef = [0.0] * len(full.cS)
+            for sl in (int(o) for o in full.order[:int(full.k)]):
+                coef[sl] = 1e-3
+            ds.set_array("cS", coef)
+            ds.set_array("cY", coef)
+            ds.set(cg=-1.0, converged=0.0)
         ms_entry = time_it(fn)
         kk = int(ds.read().k)
         ms = ms_entry
@@ -315,11 +332,6 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
             finally:
                 lib.cdll.dd4ml_debug_kspace(1)
                 ds.state.copy_(state_copy)
-        if name == "dd4ml_tr_apply":
-            # the direction pass only streams the pairs whose coefficients are non-zero (a Cauchy-point or
-            # first-order step streams none): count what this launch really read
-            full = ds.read(full=True)
-            kk = sum(1 for sl in (int(o) for o in full.order[:kk]) if full.cS[sl] != 0.0 or full.cY[sl] != 0.0)
         byt = algorithmic_bytes(name, n, kk)
         out[name] = {"n": n, "k": kk, "ms": ms, "bytes": byt, "achieved": byt / ms / 1e6,
                      "frac": byt / ms / 1e6 / peak_gbs, "ms_entry_with_kspace_kernel": ms_entry,

@@ -17,7 +17,9 @@ peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 names = ["dd4ml_lssr1_begin", "dd4ml_tr_propose", "dd4ml_tr_apply", "dd4ml_tr_decide", "dd4ml_lssr1_eval",
          "dd4ml_lssr1_trial"]
-print("| n | k | working set | " + " | ".join(n.replace("dd4ml_", "") + " (us, frac)" for n in names) + " |")
+print("Cells: entry point us (streaming kernel + k-space kernel) / streaming kernel alone us, fraction of the "
+      "measured copy peak of the streaming kernel.\n")
+print("| n | k | working set | " + " | ".join(n.replace("dd4ml_", "") for n in names) + " |")
 print("|---:|---:|---|" + "---:|" * len(names))
 for n in [217354, 1 << 20, 1 << 22, 1 << 24, 1 << 26, 1 << 28]:
     for k in (3, 5, 10):
@@ -26,7 +28,8 @@ for n in [217354, 1 << 20, 1 << 22, 1 << 24, 1 << 26, 1 << 28]:
         cells = []
         for nm in names:
             v = out.get(nm)
-            cells.append("—" if v is None else f"{v['ms'] * 1e3:.1f}, {v['frac']:.2f}")
+            cells.append("—" if v is None else
+                         f"{v['ms_entry_with_kspace_kernel'] * 1e3:.1f} / {v['ms'] * 1e3:.1f}, {v['frac']:.2f}")
         tag = f"{ws / 1e6:.0f} MB" + (" (L2)" if ws < 120e6 else "")
         ln = f"2^{n.bit_length() - 1}" if n & (n - 1) == 0 else str(n)
         print(f"| {ln} | {k} | {tag} | " + " | ".join(cells) + " |", flush=True)
