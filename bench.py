@@ -321,7 +321,7 @@ def large_n_roofline(device, kernel, peak_gbs, peak_src, n=1 << 26, k=3, iters=2
         kk = int(ds.read().k)
         ms = ms_entry
         if name in two_kernel:
-            # these entry points are TWO kernels: the HBM-bound streaming reduction and the one-warp,
+            # these entry points are TWO kernels: the HBM-bound streaming reduction and the one-CTA,
             # latency-bound k-space kernel behind it.  The roofline fraction is the streaming kernel's
             # (timed alone: k-space kernel switched off through the library's measurement hook); the
             # whole entry point is reported next to it.
@@ -597,7 +597,7 @@ def run_reference(args):
         "impl": "reference", "metric": spec["metric"], "value": r["value"], "unit": spec["unit"], "n_gpus": n,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.config == "pinn_apts_p" else "f32",
-        "data": "synthetic", "config": workload_config(args.config, n),
+        "data": "synthetic", "config": dict(workload_config(args.config, n), labels=args.labels),
         "cpu_baseline": {"value": r["value"], "unit": spec["unit"], "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": spec["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -139,7 +139,7 @@ class Lib:
 
 
 # kernels launched per entry point
-# (the reduction kernel + the one-warp k-space kernel for the entry points that solve in k-space)
+# (the reduction kernel + the one-CTA k-space kernel for the entry points that solve in k-space)
 _LAUNCHES = {"state_init": 2, "lsr1_B": 3, "tr_propose": 2, "lssr1_begin": 2, "tr_decide": 2, "lsr1_update": 2,
              "version": 0, "error_string": 0, "debug_kspace": 0}
 

@@ -1,4 +1,4 @@
-// tr_propose: ||g||, S^T g, Y^T g in one pass + k-space sub-problem solve in the last CTA.
+// tr_propose: ||g||, S^T g, Y^T g in one pass + k-space sub-problem solve in the k-space kernel launched behind it.
 #include "tma.cuh"
 
 namespace {

@@ -9,7 +9,7 @@
 //   * a deterministic two-stage finish: per-CTA partials + "last CTA done" ticket, the
 //     last CTA sums the partials (one warp per column, a fixed tree for a given grid) and
 //     stores the sums in the device state block; the k-space work on them (L-SR1 update chain,
-//     OBS / dogleg solve ...) runs in the one-warp k-space kernel that is enqueued right behind
+//     OBS / dogleg solve ...) runs in the one-CTA k-space kernel that is enqueued right behind
 //     with programmatic dependent launch (kspace_task.h) -- no host round trip.
 // The Ops below fuse what the reference does with 10-40 ATen launches per TR step.
 #include <cuda_runtime.h>

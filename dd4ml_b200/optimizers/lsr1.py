@@ -9,7 +9,7 @@ pair), instead of the reference's (n x m) row-major matrices whose column shift 
 2 n (m-1) reads+writes per accepted pair (lsr1.py:122-127).  Psi and M^{-1} are never
 materialised in n-space: the k x k Gram blocks S^T S, S^T Y, Y^T Y are kept in the
 device state block and everything the reference derives from Psi (precompute, B(v)
-inside update_memory, OBS) is evaluated from them in the last CTA of the fused
+inside update_memory, OBS) is evaluated from them in the k-space kernel behind the fused
 reduction kernels (csrc/kspace.h).
 """
 from __future__ import annotations

@@ -5,7 +5,7 @@ Device work per step:
 
     lssr1_begin  s = w - old_w, y = g - prev_g, ALL reductions of update_memory and of the
                  sub-problem in one pass over (w, old_w, g, prev_g, S, Y); the candidate pair
-                 goes to the spare ring slot; old_w <- w, prev_g <- g; the last CTA runs the
+                 goes to the spare ring slot; old_w <- w, prev_g <- g; the k-space kernel behind it runs the
                  acceptance chain, the Gram/gamma update, the L-SR1/OBS/dogleg solve, the
                  clip-to-radius and the descent flip
     tr_apply     p = cg g + sum_j (cS_j S_j + cY_j Y_j)            (direction, max|p|)

@@ -2,7 +2,7 @@
 
 One TR iteration is three fused kernels around the (untouched, PyTorch) closure:
 
-    tr_propose   ||g||, S^T g, Y^T g in one read of (g, S, Y); the last CTA solves the
+    tr_propose   ||g||, S^T g, Y^T g in one read of (g, S, Y); the k-space kernel behind it solves the
                  sub-problem in k-space (first-order, or L-SR1 + OBS + optional dogleg)
     tr_apply     p = cg g + sum_j (cS_j S_j + cY_j Y_j),  w += p        (one read, one write)
     <closure>    trial loss / gradient (PyTorch forward + backward)

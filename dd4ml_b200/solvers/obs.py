@@ -1,7 +1,7 @@
 """OBS (orthonormal-basis SR1) trust-region sub-problem solver, drop-in name for
 ``dd4ml.solvers.obs.OBS`` (obs.py:26-254).
 
-On the hot path the OBS computation is not a separate call: it runs in the one-warp k-space
+On the hot path the OBS computation is not a separate call: it runs in the one-CTA k-space
 kernel behind ``tr_propose`` / ``lssr1_begin`` (csrc/kspace.h ``tr_solve``), fed by the Gram
 blocks of the L-SR1 pairs.  This class keeps the reference's entry points:
 ``solve_tr_subproblem(g, delta, gamma, Psi, Minv)`` and ``ComputeSBySMW(tau, g, PsiTg, Psi, Minv,

@@ -54,14 +54,14 @@ int dd4ml_state_link(double* dst, int dst_off, const double* src, int src_off, d
                      void* stream);
 
 /* ---- TR.step, optimizers/tr.py:138-222 -------------------------------------------------
- * propose: ||g|| (2 or inf), S^T g, Y^T g in one pass; the last CTA then solves the
+ * propose: ||g|| (2 or inf), S^T g, Y^T g in one pass; the k-space kernel enqueued behind it then solves the
  *   sub-problem in k-space (utility/optimizer_utils.py:197-307, optimizers/lsr1.py:146-198,
  *   solvers/obs.py:46-254) and leaves the step descriptor in `state`.
  *   mode 0 = TR, 1 = LSSR1_TR (clip + descent flip, lssr1_tr.py:563-587), 2 = coefficients of
  *   LSR1.B(v) (g = v), 3 = OBS.ComputeSBySMW for tau = state.tau (obs.py:175-182).
  * apply:   p = cg*g + sum_j cS_j S_j + cY_j Y_j;  optionally w += p  (tr.py:106-131,179).
  * decide:  rho test (tr.py:186-191); accepted: y = g_trial - g_old, candidate pair
- *   reductions, g_out <- g_trial, L-SR1 update chain + radius update in the last CTA
+ *   reductions, g_out <- g_trial, L-SR1 update chain + radius update in the k-space kernel
  *   (lsr1.py:53-144, tr.py:193-214); rejected: w -= p, radius shrink (tr.py:216-222).
  *   loss_out (nullable): device-side select of what TR.step returns -- loss_out <- accepted ?
  *   trial_loss : loss and, when g_out != g_old, g_out <- g_old on rejection -- so the host needs no
@@ -175,16 +175,16 @@ int dd4ml_gather_rows(void* dst, const void* src, const int64_t* idx, int64_t nr
                       int64_t row_bytes, int64_t src_rows, void* stream);
 
 /* ---- LSR1.update_memory, optimizers/lsr1.py:53-144: candidate reductions in one pass (the
- * pair is written to the spare ring slot), acceptance chain + Gram/gamma update in the last CTA */
+ * pair is written to the spare ring slot), acceptance chain + Gram/gamma update in the k-space kernel */
 int dd4ml_lsr1_update(double* state, double* ws, const void* s, const void* y, void* S, void* Y,
                       int64_t n, int64_t ld, int vt, int ht, int kcap, void* stream);
 
 /* ---- LSR1.B, optimizers/lsr1.py:181-198: out = gamma v + Psi (Minv \ Psi^T v) -------------
- * two launches: reduce (S^T v, Y^T v) + k-space solve in the last CTA, then the output pass. */
+ * two launches: reduce (S^T v, Y^T v) + k-space kernel, then the output pass. */
 int dd4ml_lsr1_B(double* state, double* ws, const void* v, const void* S, const void* Y, void* out,
                  int64_t n, int64_t ld, int vt, int ht, int kcap, void* stream);
 
-/* ---- measurement hook: switch the one-warp k-space kernel that follows tr_propose / lssr1_begin /
+/* ---- measurement hook: switch the one-CTA k-space kernel that follows tr_propose / lssr1_begin /
  * tr_decide / lsr1_update off (0) or on (1) so that the streaming reduction kernel can be timed alone;
  * returns the previous setting.  Results are not post-processed while it is off. */
 int dd4ml_debug_kspace(int on);

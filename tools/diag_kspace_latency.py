@@ -1,4 +1,4 @@
-"""Diagnostics (GPU): latency of the entry points that end in the one-warp k-space kernel
+"""Diagnostics (GPU): latency of the entry points that end in the one-CTA k-space kernel
 (lssr1_begin, tr_propose) at the bench-native vector length, for k = 3 / 5 / 10 stored pairs:
 back to back (instruction cache warm) and right after unrelated kernels (the closure's forward /
 backward: instruction cache cold), CUDA events around the single call, plus the solver's own
