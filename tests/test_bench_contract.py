@@ -55,3 +55,20 @@ def test_reference_arm_runs_two_gloo_subdomain_processes():
     d = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][-1])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "reference"
     assert "2 gloo process" in d["cpu_baseline"]["sample"] and d["value"] > 0
+
+
+def test_reference_arm_under_the_real_torchrun_launcher():
+    """The driver's launch for N > 1: `python -m torch.distributed.run --nproc-per-node 2 bench.py --impl
+    reference`.  torchrun exports TORCHELASTIC_USE_AGENT_STORE, under which a child process group would never
+    start its own TCPStore -- the arm must scrub the launcher's environment for its gloo subdomain processes."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "dd4ml")):
+        return
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--config", "pinn_apts_p", "--steps", "2", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1                                        # rank 0 alone prints
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0

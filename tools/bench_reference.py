@@ -166,9 +166,16 @@ def run(config: str, n: int, steps: int, warmup: int, per_rank_batch: int, overr
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    env_keep = {k: os.environ.pop(k) for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT",
-                                                 "GROUP_RANK", "LOCAL_WORLD_SIZE", "TORCHELASTIC_RUN_ID")
-                if k in os.environ}
+    # Under torchrun the children must not inherit the launcher's rendezvous: with TORCHELASTIC_USE_AGENT_STORE
+    # set, rank 0 of the children's own gloo group would not start its TCPStore (it expects the elastic agent to
+    # host it) and every child waits forever.
+    launcher_keys = [k for k in os.environ
+                     if k.startswith("TORCHELASTIC_") or k in (
+                         "RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "ROLE_RANK",
+                         "ROLE_NAME", "LOCAL_WORLD_SIZE", "GROUP_WORLD_SIZE", "ROLE_WORLD_SIZE", "NODE_RANK",
+                         "TORCH_NCCL_ASYNC_ERROR_HANDLING")]
+    env_keep = {k: os.environ.pop(k) for k in launcher_keys}
+    env_keep["OMP_NUM_THREADS"] = os.environ.get("OMP_NUM_THREADS", "")
     os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ["CUDA_VISIBLE_DEVICES"] = ""            # the reference arm is the CPU path
     try:
@@ -176,11 +183,27 @@ def run(config: str, n: int, steps: int, warmup: int, per_rank_batch: int, overr
                                                    threads, q)) for r in range(n)]
         for p in procs:
             p.start()
-        out = q.get(timeout=3600)
+        out, waited = None, 0.0
+        while out is None:                      # a child that died must not leave the parent waiting
+            try:
+                out = q.get(timeout=5.0)
+            except Exception:  # noqa: BLE001  (queue.Empty)
+                waited += 5.0
+                dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+                if dead or waited > 3600:
+                    for p in procs:
+                        if p.is_alive():
+                            p.terminate()
+                    raise RuntimeError(f"reference arm: worker exit codes {dead} after {waited:.0f} s")
         for p in procs:
             p.join(timeout=120)
     finally:
+        omp = env_keep.pop("OMP_NUM_THREADS")
         os.environ.update(env_keep)
+        if omp:
+            os.environ["OMP_NUM_THREADS"] = omp
+        else:
+            os.environ.pop("OMP_NUM_THREADS", None)
         os.environ.pop("CUDA_VISIBLE_DEVICES", None)
     out.update(cores=threads * n, threads_per_process=threads, processes=n)
     return out
