@@ -1,5 +1,4 @@
-"""CPU check of dd4ml_b200/csrc/kspace.h (the k-space routines the CUDA kernels run in
-their last CTA), compiled for the host by tests/hostshim, against the oracle and the
+"""CPU check of dd4ml_b200/csrc/kspace.h (the routines of the k-space kernel), compiled for the host by tests/hostshim, against the oracle and the
 reference goldens.  No GPU, no product code path: this only validates shared source."""
 import ctypes
 import math
@@ -266,8 +265,8 @@ def test_apts_control_rules(shim):
 @pytest.mark.parametrize("dog", [False, True])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_second_order_all_memory_sizes_vs_fp64_oracle(shim, k, dog, seed):
-    """k = 1..5 run the register-resident solvers (kspace_small.h), k >= 6 the generic ones; both
-    against the oracle evaluated in fp64 on the same (fp32) data."""
+    """Every memory length up to the reference's default of 10 (k <= 3 takes the one-rotation-per-round Jacobi
+    schedule, k >= 4 the round-robin one) against the oracle evaluated in fp64 on the same (fp32) data."""
     lib, lay = shim
     torch.manual_seed(100 + k + 1000 * seed)
     n = 400
