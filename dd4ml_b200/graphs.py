@@ -23,6 +23,7 @@ import torch
 
 ENABLED = os.environ.get("DD4ML_B200_CUDA_GRAPHS", "1") != "0"
 MAX_ADDRESSES = 3     # in-place graphs per batch shape before falling back to a private input copy
+MAX_SHAPES = 4        # batch shapes kept (the Trainer's batch-size growth loop keeps producing new ones)
 
 
 class _Entry:
@@ -112,7 +113,14 @@ class GraphedEval:
             self.cache.clear()                   # parameters were re-bound: drop every stale graph
         if key in self.failed:
             return self._eval(inputs, labels)
-        ents = self.cache.setdefault(key, [])
+        ents = self.cache.get(key)
+        if ents is None:
+            while len(self.cache) >= MAX_SHAPES:         # oldest shape first (dicts keep insertion order)
+                old = next(iter(self.cache))
+                if self._hot is not None and any(self._hot[6] is x for x in self.cache[old]):
+                    self._hot = None
+                del self.cache[old]                      # frees the graphs and, with them, their memory pool
+            ents = self.cache[key] = []
         ip, lp = inputs.data_ptr(), labels.data_ptr()
         e = next((x for x in ents if not x.private and x.static_in.data_ptr() == ip and x.static_lab.data_ptr() == lp),
                  None)

@@ -94,6 +94,29 @@ def test_apts_d_fed_through_prefetcher_ring_matches_resident_batches():
             assert 1 <= len(ents) <= 2 and not any(e.private for e in ents)
 
 
+def test_closure_graph_cache_is_bounded_over_changing_batch_sizes(monkeypatch):
+    """The Trainer's batch-size growth loop (trainer.py:516-566) keeps producing new batch shapes: the closure
+    graphs of old shapes are dropped (at most graphs.MAX_SHAPES kept) and results equal the eager closures."""
+    from dd4ml_b200 import graphs
+    g = load_golden("apts_d_tr_fo_ws1")
+    X, Y = torch.from_numpy(g["X"]).to(DEV), torch.from_numpy(g["Y"]).to(DEV)
+    sizes = [32, 40, 48, 56, 64, 72, 32, 72]
+
+    def run():
+        from test_gpu_optimizers import _apts, cfg
+        model = FFNN(36, [12, 12], 10)
+        set_flat(model, torch.from_numpy(g["w0"]))
+        opt = _apts("d", model.to(DEV), "tr", "tr", cfg(), foc=True)
+        return [float(opt.step(X[:b], Y[:b])) for b in sizes], opt
+
+    graphed, opt = run()
+    for ev in (v for v in vars(opt).values() if isinstance(v, graphs.GraphedEval)):
+        assert 1 <= len(ev.cache) <= graphs.MAX_SHAPES and ev.captures >= len(set(sizes))
+    monkeypatch.setattr(graphs, "ENABLED", False)
+    eager, _ = run()
+    assert graphed == eager
+
+
 def test_host_batch_prefetcher_delivers_every_batch_in_order():
     from dd4ml_b200.dataloaders import HostBatchPrefetcher
     gen = torch.Generator().manual_seed(1)
