@@ -437,17 +437,17 @@ def run_config5_all():
     run_pinn_literal("apts_pinn_literal_ws2", 2, 10, 29644)
 
 
-def run_kernel_level(name):
+def run_kernel_level(name, ms=(1, 3, 5), seed=7):
     """Direct calls of LSR1.update_memory / precompute / B and solve_tr_second_order on
     synthetic (s, y) pairs: y = A s for a fixed indefinite diagonal-plus-low-rank A."""
-    torch.manual_seed(7)
+    torch.manual_seed(seed)
     n = 512
     diag = torch.linspace(-0.5, 3.0, n)
     Ulr = torch.randn(n, 4) / math.sqrt(n)
     A = lambda v: diag * v + Ulr @ (Ulr.t() @ v)
     out = {}
     idx = 0
-    for m in (1, 3, 5):
+    for m in ms:
         hess = LSR1(gamma=1.0, memory_length=m, tol=1e-6)
         accepted = []
         for j in range(m + 2):
@@ -576,6 +576,10 @@ def main():
         run_apts("apts_d_tr_fo_ws8", "apts_d", 8, "tr", "tr", False, False, 3, 8, port=29651)
         run_apts("apts_d_lssr1_fo_ws8", "apts_d", 8, "lssr1_tr", "lssr1_tr", False, False, 3, 8, port=29652)
         return
+    if "--only-kernel-large" in sys.argv:
+        torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
+        run_kernel_level("kernel_level_m8_m10", ms=(8, 10), seed=11)
+        return
     if "--only-samplers" in sys.argv:
         run_samplers("samplers")
         return
@@ -586,6 +590,7 @@ def main():
         return
     torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
     run_kernel_level("kernel_level")
+    run_kernel_level("kernel_level_m8_m10", ms=(8, 10), seed=11)     # up to the reference's default memory length
     run_plain("tr_fo", lambda m: TR(m.parameters(), **tr_kwargs(False, False)), 30)
     run_plain("tr_fo_inf", lambda m: TR(m.parameters(), **tr_kwargs(False, False, math.inf)), 12)
     run_plain("tr_so", lambda m: TR(m.parameters(), **tr_kwargs(True, False)), 30)

@@ -58,7 +58,7 @@ def _replay_updates(gold, m, hess_gpu, hess_cpu, idx0):
     idx = idx0
     for _ in range(m + 2):
         s, y = torch.from_numpy(gold[f"upd{idx}_s"]), torch.from_numpy(gold[f"upd{idx}_y"])
-        hess_gpu.update_memory(s.to(DEV), y.to(DEV))
+        hess_gpu.update_memory(s.to(DEV, hess_gpu.dtype), y.to(DEV, hess_gpu.dtype))
         if hess_cpu is not None:
             hess_cpu.update(s, y)
             hess_cpu.precompute()
@@ -117,6 +117,50 @@ def test_second_order_solve(m, dog, delta):
     pe_ref = abs(float(gold[key + "_pred"]) - float(pred64)) / max(abs(float(pred64)), 1e-12)
     # (pred also carries sigma*, which the reference iterates in float32 and the yardstick in float64: factor 3)
     assert float(pred) == pytest.approx(float(gold[key + "_pred"]), rel=1e-5 + 3 * pe_ref, abs=1e-9)
+
+
+@pytest.mark.parametrize("m", [8, 10])
+@pytest.mark.parametrize("dog", [False, True])
+@pytest.mark.parametrize("delta", [0.01, 0.3, 5.0, 100.0])
+def test_second_order_solve_at_the_reference_default_memory_length(m, dog, delta):
+    """8 and 10 stored pairs (10 = the reference's default memory_length) through the KMAX = 8 / 10 kernels and
+    the four-warp k-space kernel, against the UNMODIFIED reference (tests/golden/kernel_level_m8_m10.npz): the
+    reference's update chain is replayed pair by pair (acceptance, gamma, ring order), then the 12 solves that do
+    not depend on LAPACK's eigenvector signs are compared with the reference's float32 step at 1e-5 + 1.5 e_ref;
+    the 4 sign-sensitive delta = 100 solves are run in float64 and compared with the float64 oracle under the
+    documented sign convention (same rule as tests/test_kspace_host.py)."""
+    gold = load_golden("kernel_level_m8_m10")
+    idx0 = {8: 0, 10: 10}[m]
+    key = f"so_m{m}_dog{int(dog)}_d{delta}"
+    g = torch.from_numpy(gold[key + "_g"])
+    S, Y, gamma = torch.from_numpy(gold[key + "_S"]), torch.from_numpy(gold[key + "_Y"]), float(gold[key + "_gamma"])
+    hc64 = oracle_memory(S, Y, gamma, torch.float64)
+    p64, pred64 = solve_second_order(g.double(), torch.norm(g.double()), delta, hc64, 1e-6, dogleg=dog, eig_sign="canonical")
+    info = {}
+    solve_second_order(g, torch.norm(g), delta, oracle_memory(S, Y, gamma, torch.float32), 1e-6, dogleg=dog,
+                       eig_sign="canonical", info=info)
+    sensitive = sigma_spread(info, delta, gamma) > 1e-6
+    assert sensitive == (delta == 100.0)
+    dtype = torch.float64 if sensitive else torch.float32
+    h = LSR1(gamma=1.0, memory_length=m, tol=1e-6, device=DEV, dtype=dtype)
+    for idx in _replay_updates(gold, m, h, None, idx0):
+        assert float(h.gamma) == pytest.approx(float(gold[f"upd{idx}_gamma"]), rel=1e-5)
+    assert len(h._S) == m
+    assert rel_err(h.S.cpu().float(), S) == 0.0 and rel_err(h.Y.cpu().float(), Y) == 0.0      # ring order == reference columns
+    obs = dd4ml_b200.OBS()
+    gd = g.to(DEV, dtype)
+    p, pred = solve_tr_second_order(gd, torch.norm(gd), delta, h, obs, 1e-6, dogleg=dog)
+    if not sensitive:
+        e_ref = rel_err(gold[key + "_p"], p64)
+        assert rel_err(p.cpu(), gold[key + "_p"]) < 1e-5 + 1.5 * e_ref, (e_ref, rel_err(p.cpu(), gold[key + "_p"]))
+        assert float(pred) == pytest.approx(float(gold[key + "_pred"]), rel=2e-5, abs=1e-9)
+    else:
+        # the float64 run derives gamma from the float32 pairs in float64 (1e-7 from the reference's float32
+        # gamma): the yardstick uses the same gamma
+        hcg = oracle_memory(S, Y, float(h.gamma), torch.float64)
+        pg, predg = solve_second_order(g.double(), torch.norm(g.double()), delta, hcg, 1e-6, dogleg=dog, eig_sign="canonical")
+        assert rel_err(p.cpu(), pg) < 1e-6
+        assert float(pred) == pytest.approx(float(predg), rel=1e-6, abs=1e-12)
 
 
 GOLDEN_TRAJ = ("tr_so", "tr_so_dogleg", "lssr1_so_dog0", "lssr1_so_dog1", "lssr1_paper")

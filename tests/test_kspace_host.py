@@ -174,6 +174,49 @@ def test_second_order_solve_vs_oracle_and_reference(shim, m, dog, delta):
         assert rel_err(p, gold[key + "_p"]) < 2e-4
 
 
+@pytest.mark.parametrize("m", [8, 10])
+@pytest.mark.parametrize("dog", [False, True])
+@pytest.mark.parametrize("delta", [0.01, 0.3, 5.0, 100.0])
+def test_second_order_solve_at_the_reference_default_memory_length(shim, m, dog, delta):
+    """8 and 10 stored pairs (10 = the reference's default `memory_length`, lsr1.py:24) against the UNMODIFIED
+    reference (tests/golden/kernel_level_m8_m10.npz).  12 of the 16 solves do not depend on LAPACK's eigenvector
+    signs: compared with the reference's float32 step at 1e-5 + 1.5 e_ref (e_ref = the reference's own distance
+    from the float64 evaluation of its algorithm).  The 4 delta = 100 solves are sign sensitive (the start of
+    the Newton iteration moves with the signs; for m = 10 the canonical signs put it on the pole -lambda_min,
+    where float32 Newton stagnates for its 200 iterations and the step is rounding noise in any precision):
+    those are compared in float64 with the float64 oracle under the documented sign convention."""
+    from _helpers import oracle_memory, sigma_spread
+    lib, lay = shim
+    gold = load_golden("kernel_level_m8_m10")
+    key = f"so_m{m}_dog{int(dog)}_d{delta}"
+    S, Y = torch.from_numpy(gold[key + "_S"]), torch.from_numpy(gold[key + "_Y"])
+    gamma = float(gold[key + "_gamma"])
+    g = torch.from_numpy(gold[key + "_g"])
+    assert S.shape[1] == m
+    hc64 = oracle_memory(S, Y, gamma, torch.float64)
+    p64, pred64 = solve_second_order(g.double(), torch.norm(g.double()), delta, hc64, 1e-6, dogleg=dog,
+                                     eig_sign="canonical")
+    info = {}
+    solve_second_order(g, torch.norm(g), delta, oracle_memory(S, Y, gamma, torch.float32), 1e-6, dogleg=dog,
+                       eig_sign="canonical", info=info)
+    sensitive = sigma_spread(info, delta, gamma) > 1e-6
+    assert sensitive == (delta == 100.0)
+    hs = HostState(lib, lay, m=m, delta=delta, second_order=1, dogleg=int(dog))
+    hs.load_pairs(S, Y, gamma)
+    if not sensitive:
+        p = hs.solve(g, is_float=1)
+        assert hs.get("err") == 0
+        e_ref = rel_err(gold[key + "_p"], p64)
+        assert e_ref < 2e-6
+        assert rel_err(p, gold[key + "_p"]) < 1e-5 + 1.5 * e_ref
+        assert hs.get("pred") == pytest.approx(float(gold[key + "_pred"]), rel=2e-5, abs=1e-9)
+    else:
+        p = hs.solve(g.double(), is_float=0)
+        assert hs.get("err") == 0
+        assert rel_err(p, p64) < 1e-8
+        assert hs.get("pred") == pytest.approx(float(pred64), rel=1e-7, abs=1e-12)
+
+
 def test_update_chain_matches_reference(shim):
     lib, lay = shim
     gold = load_golden("kernel_level")
