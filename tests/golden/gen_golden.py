@@ -554,6 +554,14 @@ def run_samplers(name):
     print(f"wrote {path}  ({os.path.getsize(path) // 1024} KB)")
 
 
+def run_lssr1_m10():
+    """LSSR1_TR with the reference's default memory length of 10 (second order + dogleg), 30 steps."""
+    from dd4ml.utility import get_lssr1_tr_hparams
+    hp = get_lssr1_tr_hparams(apts_cfg("lssr1_tr", "lssr1_tr", True, True, 10))
+    hp["sync"] = False
+    run_plain("lssr1_so_dog1_m10", lambda m: LSSR1_TR(m.parameters(), **hp), 30, data_seed=2010)
+
+
 def main():
     if "--only-config5" in sys.argv:
         torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
@@ -579,6 +587,7 @@ def main():
     if "--only-kernel-large" in sys.argv:
         torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
         run_kernel_level("kernel_level_m8_m10", ms=(8, 10), seed=11)
+        run_lssr1_m10()
         return
     if "--only-samplers" in sys.argv:
         run_samplers("samplers")
@@ -591,6 +600,7 @@ def main():
     torch.set_num_threads(int(os.environ["OMP_NUM_THREADS"]))
     run_kernel_level("kernel_level")
     run_kernel_level("kernel_level_m8_m10", ms=(8, 10), seed=11)     # up to the reference's default memory length
+    run_lssr1_m10()
     run_plain("tr_fo", lambda m: TR(m.parameters(), **tr_kwargs(False, False)), 30)
     run_plain("tr_fo_inf", lambda m: TR(m.parameters(), **tr_kwargs(False, False, math.inf)), 12)
     run_plain("tr_so", lambda m: TR(m.parameters(), **tr_kwargs(True, False)), 30)

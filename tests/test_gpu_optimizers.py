@@ -172,6 +172,7 @@ def test_flat_views_survive_set_to_none():
     ("lssr1_so_dog1_s1", dict(glob_second_order=True, glob_dogleg=True)),
     ("lssr1_so_dog1_s2", dict(glob_second_order=True, glob_dogleg=True)),
     ("lssr1_so_dog1_s3", dict(glob_second_order=True, glob_dogleg=True)),
+    ("lssr1_so_dog1_m10", dict(glob_second_order=True, glob_dogleg=True, mem_length=10)),
     ("lssr1_paper", dict(glob_second_order=True, paper_tr_update=True))])
 def test_lssr1_matches_oracle_and_reference(name, kw):
     g = load_golden(name)
@@ -181,7 +182,8 @@ def test_lssr1_matches_oracle_and_reference(name, kw):
     hp["sync"] = False
     opt = LSSR1_TR(model.parameters(), **hp)
     closure = make_closure(opt, model, X.to(DEV), Y.to(DEV))
-    ohp = oracle.lssr1_hparams(0.1, 0.01, 1.0, mem_length=3, second_order=kw.get("glob_second_order", True),
+    ohp = oracle.lssr1_hparams(0.1, 0.01, 1.0, mem_length=kw.get("mem_length", 3),
+                               second_order=kw.get("glob_second_order", True),
                                dogleg=kw.get("glob_dogleg", False), paper_tr_update=kw.get("paper_tr_update", False))
     ohp.pop("sync")
     oopt = oracle.LSSR1TROracle(**ohp, eig_sign="canonical")

@@ -109,9 +109,11 @@ def test_tr_trajectory_matches_reference(name, so, dog, norm):
     ("lssr1_so_dog1_s1", dict(second_order=True, dogleg=True)),
     ("lssr1_so_dog1_s2", dict(second_order=True, dogleg=True)),
     ("lssr1_so_dog1_s3", dict(second_order=True, dogleg=True)),
+    ("lssr1_so_dog1_m10", dict(second_order=True, dogleg=True, mem_length=10)),
     ("lssr1_paper", dict(second_order=True, paper_tr_update=True))])
 def test_lssr1_trajectory_matches_reference(name, kw):
-    hp = oracle.lssr1_hparams(0.1, 0.01, 1.0, mem_length=3, **kw)
+    kw = dict(kw)
+    hp = oracle.lssr1_hparams(0.1, 0.01, 1.0, mem_length=kw.pop("mem_length", 3), **kw)
     hp.pop("sync")
     _run_plain(name, lambda: oracle.LSSR1TROracle(**hp))
 
