@@ -15,7 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def test_parity_suite_through_tma_kernels():
     env = dict(os.environ, DD4ML_B200_TMA_MIN_N="0", DD4ML_B200_TMA_MODE="1")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_kernels.py"),
-                        os.path.join(HERE, "test_gpu_optimizers.py"), os.path.join(HERE, "test_gpu_configs.py"), "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"],
+                        os.path.join(HERE, "test_gpu_optimizers.py"), os.path.join(HERE, "test_gpu_configs.py"), "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider",
+                        # (the extra-seed / memory-length-10 trajectory goldens spend their time in CPU oracle
+                        #  ensembles; their kernels are covered in this mode by test_gpu_kernels.py)
+                        "-k", "not (matches_oracle_and_reference and (_s1 or _s2 or _s3 or m10))"],
                        env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
 
